@@ -1,0 +1,806 @@
+// libsbn_b200 engine: device buffers, staging, kernel launches and the C ABI of
+// include/sbn_b200.h.  Replaces the reference's Engine / FatBeagle pair
+// (src/engine.cpp, src/fat_beagle.cpp) and the BEAGLE instance they drive.
+//
+// There is deliberately no CPU path in this file: without a CUDA device every
+// entry point fails.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+#include "kernels.cuh"
+#include "model.hpp"
+#include "rooted.hpp"
+#include "tree_program.hpp"
+
+namespace sbnb {
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define SBNB_CUDA(call)                                                                     \
+  do {                                                                                      \
+    cudaError_t status_ = (call);                                                           \
+    if (status_ != cudaSuccess) {                                                           \
+      const int code_ = (status_ == cudaErrorMemoryAllocation)                              \
+                            ? SBNB_ERR_OUT_OF_MEMORY                                        \
+                            : ((status_ == cudaErrorNoDevice ||                             \
+                                status_ == cudaErrorInsufficientDriver)                     \
+                                   ? SBNB_ERR_NO_DEVICE                                     \
+                                   : SBNB_ERR_CUDA);                                        \
+      ::sbnb::Fail(code_, std::string(#call) + ": " + cudaGetErrorString(status_));         \
+    }                                                                                       \
+  } while (0)
+
+// Device allocation that grows on demand and is reused between calls.
+template <typename T>
+class DeviceArray {
+ public:
+  DeviceArray() = default;
+  DeviceArray(const DeviceArray&) = delete;
+  DeviceArray& operator=(const DeviceArray&) = delete;
+  ~DeviceArray() { cudaFree(ptr_); }
+  void Reserve(size_t count) {
+    if (count <= capacity_) return;
+    cudaFree(ptr_);
+    ptr_ = nullptr;
+    capacity_ = 0;
+    SBNB_CUDA(cudaMalloc(&ptr_, std::max<size_t>(count, 1) * sizeof(T)));
+    capacity_ = count;
+  }
+  void Upload(const T* host, size_t count, cudaStream_t stream) {
+    Reserve(count);
+    if (count) SBNB_CUDA(cudaMemcpyAsync(ptr_, host, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+  }
+  T* get() const { return ptr_; }
+  size_t capacity() const { return capacity_; }
+
+ private:
+  T* ptr_ = nullptr;
+  size_t capacity_ = 0;
+};
+
+int PadCategories(int c) {
+  int padded = 1;
+  while (padded < c) padded <<= 1;
+  return padded;
+}
+
+int EnvInt(const char* name, int fallback) {
+  const char* value = std::getenv(name);
+  return value ? std::atoi(value) : fallback;
+}
+
+}  // namespace
+
+void SetLastError(const std::string& message) { g_last_error = message; }
+
+}  // namespace sbnb
+
+using namespace sbnb;
+
+struct sbnb_engine {
+  ModelSpec spec;
+  int device = 0;
+  int sm_count = 0;
+  int taxon_count = 0;
+  int64_t pattern_count = 0;
+  int64_t tip_pitch = 0;
+  int64_t range_begin = 0, range_end = 0;
+  int categories = 1;         // C
+  int padded_categories = 1;  // power of two >= C (extra categories have weight 0)
+  int patterns_per_thread = 2;
+  cudaStream_t stream = nullptr;
+  int64_t launch_count = 0;
+  DeviceArray<uint8_t> tips;
+  DeviceArray<double> weights;
+  DeviceArray<double2> scratch;  // post-order partial arena, reused by every gradient run
+
+  ~sbnb_engine() {
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+struct sbnb_batch {
+  int tree_count = 0;
+  int taxon_count = 0;
+  int node_count = 0;  // 2n-1
+  bool rooted = false;
+  int fd_coords = 0;  // stick-breaking coordinates perturbed (0 if no FD staged)
+  int vtree_count = 0;
+  int slots = 1;
+  int last_mode = -1;
+  int64_t patterns = 0;  // pattern range of the engine when staged
+  int categories = 1;
+  // host side, kept for the O(n) finishing steps
+  std::vector<TreeProgram> programs;
+  std::vector<double> lengths;  // [T][2n-1] after detrifurcation / rate scaling / root slide
+  // device side
+  DeviceArray<PostOp> post_ops;
+  DeviceArray<PreOp> pre_ops;
+  DeviceArray<int32_t> vtree_program, vtree_model, vtree_lengths;
+  DeviceArray<ModelTables> models;
+  DeviceArray<double> d_lengths, matrices;
+  DeviceArray<double> logl_partial, grad_partial, rgrad_partial;
+  DeviceArray<double> logl, grad, rgrad;
+  // tiling of the last run
+  int chunks = 1;
+};
+
+namespace {
+
+struct LaunchPlan {
+  int tiles_total, tiles_per_chunk, chunks, grid;
+  size_t smem_bytes;
+};
+
+template <int C, int K, bool GRAD, bool RESCALE>
+LaunchPlan PlanAndLaunch(sbnb_engine* e, WalkParams p, bool launch, int chunks_override) {
+  auto kernel = TreeWalkKernel<C, K, GRAD, RESCALE>;
+  const size_t smem = static_cast<size_t>(p.slots) * K * kThreads * (sizeof(double2) * 2 + sizeof(int));
+  if (smem > 227 * 1024)
+    Fail(SBNB_ERR_INVALID_ARGUMENT, "Tree too deep for the shared-memory stack: " +
+                                        std::to_string(p.slots) + " slots.");
+  SBNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  int per_sm = 0;
+  SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
+  if (per_sm < 1) Fail(SBNB_ERR_CUDA, "TreeWalkKernel does not fit on an SM.");
+  const int resident = per_sm * e->sm_count;
+  constexpr int kTilePatterns = (kThreads / C) * K;
+  LaunchPlan plan;
+  const int64_t patterns = p.pattern_end - p.pattern_begin;
+  plan.tiles_total = static_cast<int>((patterns + kTilePatterns - 1) / kTilePatterns);
+  if (chunks_override > 0) {
+    plan.chunks = chunks_override;
+    plan.tiles_per_chunk = (plan.tiles_total + plan.chunks - 1) / plan.chunks;
+  } else {
+    // Enough (tree, chunk) work items to give every resident CTA ~4 of them.
+    int64_t want = (4LL * resident + p.vtree_count - 1) / std::max(p.vtree_count, 1);
+    want = std::max<int64_t>(1, std::min<int64_t>(want, plan.tiles_total));
+    plan.tiles_per_chunk = static_cast<int>((plan.tiles_total + want - 1) / want);
+    plan.chunks = (plan.tiles_total + plan.tiles_per_chunk - 1) / plan.tiles_per_chunk;
+  }
+  const int64_t items = static_cast<int64_t>(p.vtree_count) * plan.chunks;
+  plan.grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(items, resident)));
+  plan.smem_bytes = smem;
+  if (launch) {
+    p.tiles_total = plan.tiles_total;
+    p.tiles_per_chunk = plan.tiles_per_chunk;
+    p.chunks = plan.chunks;
+    kernel<<<plan.grid, kThreads, smem, e->stream>>>(p);
+    SBNB_CUDA(cudaGetLastError());
+    e->launch_count++;
+  }
+  return plan;
+}
+
+template <int C, int K>
+LaunchPlan DispatchModes(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
+                         int chunks_override) {
+  if (grad) {
+    return rescale ? PlanAndLaunch<C, K, true, true>(e, p, launch, chunks_override)
+                   : PlanAndLaunch<C, K, true, false>(e, p, launch, chunks_override);
+  }
+  return rescale ? PlanAndLaunch<C, K, false, true>(e, p, launch, chunks_override)
+                 : PlanAndLaunch<C, K, false, false>(e, p, launch, chunks_override);
+}
+
+template <int C>
+LaunchPlan DispatchK(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
+                     int chunks_override) {
+  switch (e->patterns_per_thread) {
+    case 1:
+      return DispatchModes<C, 1>(e, p, grad, rescale, launch, chunks_override);
+    case 4:
+      return DispatchModes<C, 4>(e, p, grad, rescale, launch, chunks_override);
+    default:
+      return DispatchModes<C, 2>(e, p, grad, rescale, launch, chunks_override);
+  }
+}
+
+LaunchPlan Dispatch(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
+                    int chunks_override) {
+  switch (e->padded_categories) {
+    case 1:
+      return DispatchK<1>(e, p, grad, rescale, launch, chunks_override);
+    case 2:
+      return DispatchK<2>(e, p, grad, rescale, launch, chunks_override);
+    case 4:
+      return DispatchK<4>(e, p, grad, rescale, launch, chunks_override);
+    case 8:
+      return DispatchK<8>(e, p, grad, rescale, launch, chunks_override);
+    case 16:
+      return DispatchK<16>(e, p, grad, rescale, launch, chunks_override);
+  }
+  Fail(SBNB_ERR_INVALID_ARGUMENT, "Unsupported category count.");
+}
+
+void CheckTrees(const sbnb_engine* e, const sbnb_tree_batch* trees, bool rooted) {
+  Require(trees != nullptr, "NULL tree batch.");
+  Require(trees->tree_count >= 0, "Negative tree count.");
+  Require(trees->tree_count == 0 || (trees->parent_ids && trees->branch_lengths),
+          "NULL parent_ids / branch_lengths.");
+  const int n = e->taxon_count;
+  if (rooted) {
+    Require(trees->node_count == 2 * n - 1,
+            "Rooted trees must be bifurcating: node_count must be 2n-1.");
+    Require(trees->tree_count == 0 || trees->rates != nullptr,
+            "Rooted evaluation needs per-branch rates (RootedTree::rates_).");
+  } else {
+    Require(trees->node_count == 2 * n - 1 || trees->node_count == 2 * n - 2,
+            "node_count must be 2n-2 (unrooted) or 2n-1 (bifurcating).");
+  }
+}
+
+// Perturbed parameter rows of the finite-difference substitution gradient,
+// in output order: GTR -> coordinates 0..4 = rates, 5..7 = frequencies
+// (fat_beagle.cpp:455-464), each as (plus, minus).
+void FiniteDifferenceRows(const ModelSpec& spec, const double* row, double delta,
+                          std::vector<std::vector<double>>* rows) {
+  rows->clear();
+  auto perturb_simplex = [&](const std::string& key) {
+    const auto [start, length] = spec.Block(key);
+    std::vector<double> y(length - 1), x(length);
+    StickBreakingInverse(row + start, length, y.data());
+    for (int idx = 0; idx < length - 1; idx++) {
+      for (int sign = +1; sign >= -1; sign -= 2) {
+        std::vector<double> yy = y;
+        yy[idx] += sign * delta;
+        StickBreaking(yy.data(), length, x.data());
+        std::vector<double> perturbed(row, row + spec.param_count);
+        std::copy(x.begin(), x.end(), perturbed.begin() + start);
+        rows->push_back(std::move(perturbed));
+      }
+    }
+  };
+  if (spec.substitution == SubstitutionKind::kGTR) {
+    perturb_simplex("GTR rates");
+    perturb_simplex("frequencies");
+  } else if (spec.substitution == SubstitutionKind::kHKY) {
+    const int kappa = spec.Block("kappa").first;
+    for (int sign = +1; sign >= -1; sign -= 2) {
+      std::vector<double> perturbed(row, row + spec.param_count);
+      perturbed[kappa] += sign * delta;
+      rows->push_back(std::move(perturbed));
+    }
+    perturb_simplex("frequencies");
+  }
+}
+
+constexpr double kFiniteDifferenceDelta = 1.e-6;  // fat_beagle.cpp:454
+
+std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params,
+                                  bool rooted, bool with_fd) {
+  CheckTrees(e, trees, rooted);
+  const ModelSpec& spec = e->spec;
+  Require(spec.param_count == 0 || params != nullptr || trees->tree_count == 0,
+          "NULL phylo model parameter matrix.");
+  SBNB_CUDA(cudaSetDevice(e->device));
+  auto batch = std::make_unique<sbnb_batch>();
+  const int T = trees->tree_count, n = e->taxon_count, N = 2 * n - 1;
+  batch->tree_count = T;
+  batch->taxon_count = n;
+  batch->node_count = N;
+  batch->rooted = rooted;
+  batch->patterns = e->range_end - e->range_begin;
+  batch->categories = e->categories;
+  const int fd_evals = with_fd ? 2 * spec.SubstitutionGradientSize() : 0;
+  batch->fd_coords = fd_evals / 2;
+  batch->vtree_count = T * (1 + fd_evals);
+  if (T == 0) return batch;
+
+  // Programs + branch lengths.
+  batch->programs.reserve(T);
+  batch->lengths.assign(static_cast<size_t>(T) * N, 0.0);
+  std::vector<PostOp> post(static_cast<size_t>(T) * (n - 1));
+  std::vector<PreOp> pre(static_cast<size_t>(T) * (n - 1));
+  int slots = 1;
+  for (int t = 0; t < T; t++) {
+    TreeProgram program = BuildTreeProgram(
+        trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1), trees->node_count, n);
+    const double* in = trees->branch_lengths + static_cast<size_t>(t) * trees->node_count;
+    double* out = batch->lengths.data() + static_cast<size_t>(t) * N;
+    std::copy(in, in + trees->node_count, out);
+    if (program.was_trifurcating) {
+      // Detrifurcate (unrooted_tree.cpp:31-35): the node that takes the old
+      // root's id and the new root both get length 0.
+      out[N - 2] = 0.0;
+      out[N - 1] = 0.0;
+    }
+    if (rooted) {
+      // fat_beagle.cpp:96-101, 507-511
+      const double* rates = trees->rates + static_cast<size_t>(t) * (N - 1);
+      for (int i = 0; i < N - 1; i++) out[i] *= rates[i];
+    }
+    std::copy(program.post.begin(), program.post.end(), post.begin() + static_cast<size_t>(t) * (n - 1));
+    std::copy(program.pre.begin(), program.pre.end(), pre.begin() + static_cast<size_t>(t) * (n - 1));
+    slots = std::max({slots, program.post_slots, program.pre_slots});
+    batch->programs.push_back(std::move(program));
+  }
+  batch->slots = slots;
+
+  // Models: one table per distinct consecutive parameter row (+ its FD rows).
+  std::vector<ModelTables> models;
+  std::vector<int32_t> vtree_program(batch->vtree_count), vtree_model(batch->vtree_count),
+      vtree_lengths(batch->vtree_count);
+  const int K = spec.param_count;
+  int previous_base_model = -1;
+  std::vector<std::vector<double>> fd_rows;
+  for (int t = 0; t < T; t++) {
+    const double* row = params + static_cast<size_t>(t) * K;
+    const bool same_as_previous =
+        t > 0 && (K == 0 || std::memcmp(row, row - K, sizeof(double) * K) == 0);
+    if (!same_as_previous) {
+      previous_base_model = static_cast<int>(models.size());
+      models.emplace_back();
+      BuildModelTables(spec, row, &models.back());
+      if (fd_evals) {
+        FiniteDifferenceRows(spec, row, kFiniteDifferenceDelta, &fd_rows);
+        for (const auto& fd_row : fd_rows) {
+          models.emplace_back();
+          BuildModelTables(spec, fd_row.data(), &models.back());
+        }
+      }
+    }
+    vtree_program[t] = t;
+    vtree_model[t] = previous_base_model;
+    vtree_lengths[t] = t;
+    for (int f = 0; f < fd_evals; f++) {
+      const int v = T + t * fd_evals + f;
+      vtree_program[v] = t;
+      vtree_model[v] = previous_base_model + 1 + f;
+      vtree_lengths[v] = t;
+    }
+  }
+
+  cudaStream_t s = e->stream;
+  batch->post_ops.Upload(post.data(), post.size(), s);
+  batch->pre_ops.Upload(pre.data(), pre.size(), s);
+  batch->vtree_program.Upload(vtree_program.data(), vtree_program.size(), s);
+  batch->vtree_model.Upload(vtree_model.data(), vtree_model.size(), s);
+  batch->vtree_lengths.Upload(vtree_lengths.data(), vtree_lengths.size(), s);
+  batch->models.Upload(models.data(), models.size(), s);
+  batch->d_lengths.Upload(batch->lengths.data(), batch->lengths.size(), s);
+  batch->matrices.Reserve(static_cast<size_t>(batch->vtree_count) * (N - 1) * e->padded_categories * 16);
+  batch->logl.Reserve(batch->vtree_count);
+  batch->grad.Reserve(static_cast<size_t>(T) * N);
+  batch->rgrad.Reserve(static_cast<size_t>(T) * N);
+  // The uploads read pageable host vectors that die with this scope.
+  SBNB_CUDA(cudaStreamSynchronize(s));
+  return batch;
+}
+
+WalkParams BaseParams(sbnb_engine* e, sbnb_batch* b) {
+  WalkParams p{};
+  p.tips = e->tips.get();
+  p.tip_pitch = e->tip_pitch;
+  p.weights = e->weights.get();
+  p.pattern_begin = e->range_begin;
+  p.pattern_end = e->range_end;
+  p.taxon_count = e->taxon_count;
+  p.post_ops = b->post_ops.get();
+  p.pre_ops = b->pre_ops.get();
+  p.vtree_program = b->vtree_program.get();
+  p.vtree_model = b->vtree_model.get();
+  p.models = b->models.get();
+  p.matrices = b->matrices.get();
+  p.slots = b->slots;
+  return p;
+}
+
+void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
+  Require(mode == SBNB_MODE_LOG_LIKELIHOOD || mode == SBNB_MODE_BRANCH_GRADIENT, "Unknown mode.");
+  SBNB_CUDA(cudaSetDevice(e->device));
+  b->last_mode = mode;
+  if (b->tree_count == 0) return;
+  const bool grad = (mode == SBNB_MODE_BRANCH_GRADIENT);
+  const int T = b->tree_count, N = b->node_count, C = e->padded_categories;
+  cudaStream_t s = e->stream;
+  const int vtrees = grad ? b->vtree_count : T;
+
+  // K1: transition matrices for every (virtual tree, edge, category).
+  {
+    const int64_t total = static_cast<int64_t>(vtrees) * (N - 1) * C;
+    const int block = 128;
+    const int grid = static_cast<int>((total + block - 1) / block);
+    TransitionMatrixKernel<<<grid, block, 0, s>>>(b->models.get(), b->vtree_model.get(),
+                                                  b->vtree_lengths.get(), b->d_lengths.get(),
+                                                  b->matrices.get(), vtrees, N - 1, N, C);
+    SBNB_CUDA(cudaGetLastError());
+    e->launch_count++;
+  }
+
+  WalkParams p = BaseParams(e, b);
+  // Base trees: logL or gradient sweep.
+  p.vtree_begin = 0;
+  p.vtree_count = T;
+  LaunchPlan plan = Dispatch(e, p, grad, rescaling, /*launch=*/false, 0);
+  const int fd_vtrees = vtrees - T;
+  LaunchPlan fd_plan{};
+  if (fd_vtrees > 0) {
+    WalkParams q = p;
+    q.vtree_begin = T;
+    q.vtree_count = fd_vtrees;
+    fd_plan = Dispatch(e, q, false, rescaling, false, 0);
+  }
+  // Partial-sum rows: [vtree][chunk][warp]; both launches share one chunk count
+  // so that a single row stride addresses the buffers.
+  const int chunks = std::max(plan.chunks, fd_vtrees > 0 ? fd_plan.chunks : 1);
+  b->chunks = chunks;
+  const size_t rows = static_cast<size_t>(vtrees) * chunks * kWarps;
+  b->logl_partial.Reserve(rows);
+  SBNB_CUDA(cudaMemsetAsync(b->logl_partial.get(), 0, rows * sizeof(double), s));
+  if (grad) {
+    const size_t grad_rows = static_cast<size_t>(T) * chunks * kWarps * N;
+    b->grad_partial.Reserve(grad_rows);
+    SBNB_CUDA(cudaMemsetAsync(b->grad_partial.get(), 0, grad_rows * sizeof(double), s));
+    if (C > 1) {
+      b->rgrad_partial.Reserve(grad_rows);
+      SBNB_CUDA(cudaMemsetAsync(b->rgrad_partial.get(), 0, grad_rows * sizeof(double), s));
+    }
+    plan = Dispatch(e, p, grad, rescaling, false, chunks);
+    e->scratch.Reserve(static_cast<size_t>(plan.grid) * (b->taxon_count - 1) *
+                       e->patterns_per_thread * 2 * kThreads);
+  }
+  p.scratch = e->scratch.get();
+  p.logl_partial = b->logl_partial.get();
+  p.grad_partial = b->grad_partial.get();
+  p.rgrad_partial = b->rgrad_partial.get();
+  Dispatch(e, p, grad, rescaling, /*launch=*/true, chunks);
+  if (fd_vtrees > 0) {
+    WalkParams q = p;
+    q.vtree_begin = T;
+    q.vtree_count = fd_vtrees;
+    Dispatch(e, q, false, rescaling, true, chunks);
+  }
+
+  // K3: fixed-order reduction of the per-(chunk, warp) partial sums.
+  {
+    const int block = 128;
+    ReducePartialsKernel<<<(vtrees + block - 1) / block, block, 0, s>>>(
+        b->logl_partial.get(), b->logl.get(), 0, vtrees, chunks * kWarps, 1);
+    SBNB_CUDA(cudaGetLastError());
+    e->launch_count++;
+    if (grad) {
+      const int64_t total = static_cast<int64_t>(T) * N;
+      const int grid = static_cast<int>((total + block - 1) / block);
+      ReducePartialsKernel<<<grid, block, 0, s>>>(b->grad_partial.get(), b->grad.get(), 0, T,
+                                                  chunks * kWarps, N);
+      SBNB_CUDA(cudaGetLastError());
+      e->launch_count++;
+      if (C > 1) {
+        ReducePartialsKernel<<<grid, block, 0, s>>>(b->rgrad_partial.get(), b->rgrad.get(), 0, T,
+                                                    chunks * kWarps, N);
+        SBNB_CUDA(cudaGetLastError());
+        e->launch_count++;
+      }
+    }
+  }
+}
+
+void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rgrad) {
+  SBNB_CUDA(cudaSetDevice(e->device));
+  Require(b->last_mode >= 0, "sbnb_batch_fetch called before sbnb_batch_run.");
+  const bool was_grad = (b->last_mode == SBNB_MODE_BRANCH_GRADIENT);
+  const int vtrees = was_grad ? b->vtree_count : b->tree_count;
+  const size_t per_tree = static_cast<size_t>(b->node_count);
+  cudaStream_t s = e->stream;
+  if (b->tree_count > 0) {
+    if (logl)
+      SBNB_CUDA(cudaMemcpyAsync(logl, b->logl.get(), vtrees * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (grad) {
+      Require(was_grad, "No gradient available: the last run was a log-likelihood run.");
+      SBNB_CUDA(cudaMemcpyAsync(grad, b->grad.get(), b->tree_count * per_tree * sizeof(double),
+                                cudaMemcpyDeviceToHost, s));
+    }
+    if (rgrad) {
+      Require(was_grad, "No gradient available: the last run was a log-likelihood run.");
+      if (e->padded_categories > 1) {
+        SBNB_CUDA(cudaMemcpyAsync(rgrad, b->rgrad.get(), b->tree_count * per_tree * sizeof(double),
+                                  cudaMemcpyDeviceToHost, s));
+      } else {
+        std::fill(rgrad, rgrad + b->tree_count * per_tree, 0.0);
+      }
+    }
+  }
+  SBNB_CUDA(cudaStreamSynchronize(s));
+}
+
+RootedView ViewOf(const sbnb_tree_batch* trees, int t, int n) {
+  const int N = 2 * n - 1;
+  RootedView view{};
+  view.branch_lengths = trees->branch_lengths + static_cast<size_t>(t) * N;
+  view.rates = trees->rates + static_cast<size_t>(t) * (N - 1);
+  view.node_heights = trees->node_heights ? trees->node_heights + static_cast<size_t>(t) * N : nullptr;
+  view.node_bounds = trees->node_bounds ? trees->node_bounds + static_cast<size_t>(t) * N : nullptr;
+  view.height_ratios =
+      trees->height_ratios ? trees->height_ratios + static_cast<size_t>(t) * (n - 1) : nullptr;
+  view.rate_count = trees->rate_count;
+  return view;
+}
+
+// The one-call forms of Engine's five methods.
+void LogLikelihoods(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params,
+                    bool rescaling, bool rooted_semantics, bool add_jacobian, double* out) {
+  Require(out != nullptr || trees->tree_count == 0, "NULL output.");
+  auto batch = Stage(e, trees, params, rooted_semantics, false);
+  Run(e, batch.get(), SBNB_MODE_LOG_LIKELIHOOD, rescaling);
+  Fetch(e, batch.get(), out, nullptr, nullptr);
+  if (add_jacobian) {
+    Require(trees->tree_count == 0 || (trees->node_heights && trees->node_bounds),
+            "Rooted log likelihoods need node_heights and node_bounds.");
+    for (int t = 0; t < trees->tree_count; t++)
+      out[t] += LogDetJacobianHeightRatios(batch->programs[t], ViewOf(trees, t, e->taxon_count));
+  }
+}
+
+void Gradients(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params, bool rescaling,
+               bool rooted, const sbnb_gradient_out* out) {
+  Require(out != nullptr, "NULL gradient output.");
+  const ModelSpec& spec = e->spec;
+  const int fd_coords = spec.SubstitutionGradientSize();
+  auto batch = Stage(e, trees, params, rooted, fd_coords > 0 && out->substitution_model != nullptr);
+  Run(e, batch.get(), SBNB_MODE_BRANCH_GRADIENT, rescaling);
+  const int T = trees->tree_count, n = e->taxon_count, N = 2 * n - 1;
+  std::vector<double> logl(batch->vtree_count), grad(static_cast<size_t>(T) * N),
+      rgrad(static_cast<size_t>(T) * N);
+  Fetch(e, batch.get(), logl.data(), grad.data(), rgrad.data());
+  if (rooted)
+    Require(T == 0 || (trees->node_heights && trees->node_bounds && trees->height_ratios),
+            "Rooted gradients need node_heights, node_bounds and height_ratios.");
+  for (int t = 0; t < T; t++) {
+    const TreeProgram& tree = batch->programs[t];
+    double* g = grad.data() + static_cast<size_t>(t) * N;
+    const double* rg = rgrad.data() + static_cast<size_t>(t) * N;
+    const double* lengths = batch->lengths.data() + static_cast<size_t>(t) * N;
+    if (out->log_likelihood) out->log_likelihood[t] = logl[t];
+    if (out->substitution_model && batch->fd_coords > 0) {
+      // Central differences; the rooted Jacobian term cancels (fat_beagle.cpp:431).
+      const double* fd = logl.data() + T + static_cast<size_t>(t) * 2 * batch->fd_coords;
+      for (int k = 0; k < batch->fd_coords; k++)
+        out->substitution_model[static_cast<size_t>(t) * batch->fd_coords + k] =
+            (fd[2 * k] - fd[2 * k + 1]) / (2. * kFiniteDifferenceDelta);
+    }
+    if (out->site_model && e->categories > 1)
+      out->site_model[t] = DiscreteSiteModelGradient(N, lengths, rg);  // fat_beagle.cpp:389-398
+    if (rooted) {
+      const RootedView view = ViewOf(trees, t, n);
+      if (out->ratios_root_height) {
+        const std::vector<double> ratios = RatioGradientOfBranchGradient(tree, view, g);
+        std::copy(ratios.begin(), ratios.end(), out->ratios_root_height + static_cast<size_t>(t) * (n - 1));
+      }
+      if (out->clock_model) {
+        const std::vector<double> clock = ClockGradient(tree, view, g);
+        std::copy(clock.begin(), clock.end(), out->clock_model + static_cast<size_t>(t) * view.rate_count);
+      }
+    } else if (out->branch_lengths) {
+      // "We want the fixed node to have a zero gradient" (fat_beagle.cpp:498-500).
+      g[tree.child1[tree.root]] = 0.0;
+      std::copy(g, g + N, out->branch_lengths + static_cast<size_t>(t) * N);
+    }
+  }
+}
+
+template <typename F>
+int Guard(F&& body) {
+  try {
+    body();
+    return SBNB_OK;
+  } catch (const Error& error) {
+    SetLastError(error.what());
+    return error.code();
+  } catch (const std::bad_alloc&) {
+    SetLastError("host allocation failed");
+    return SBNB_ERR_OUT_OF_MEMORY;
+  } catch (const std::exception& error) {
+    SetLastError(error.what());
+    return SBNB_ERR_INVALID_ARGUMENT;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sbnb_last_error(void) { return g_last_error.c_str(); }
+
+int sbnb_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+
+int sbnb_engine_create(const char* substitution, const char* site, const char* clock,
+                       int32_t taxon_count, int64_t pattern_count, const uint8_t* tip_states,
+                       const double* pattern_weights, int32_t device, sbnb_engine** out) {
+  return Guard([&] {
+    Require(out != nullptr, "NULL output handle.");
+    *out = nullptr;
+    Require(substitution && site && clock, "NULL model specification string.");
+    Require(taxon_count >= 2, "Need at least 2 taxa.");
+    Require(pattern_count >= 1, "Need at least 1 site pattern.");
+    Require(tip_states && pattern_weights, "NULL tip_states / pattern_weights.");
+    auto engine = std::make_unique<sbnb_engine>();
+    engine->spec = ModelSpec::Parse(substitution, site, clock);
+    int device_count = 0;
+    if (cudaGetDeviceCount(&device_count) != cudaSuccess || device_count < 1) {
+      cudaGetLastError();
+      Fail(SBNB_ERR_NO_DEVICE,
+           "No CUDA device available: libsbn_b200 has no CPU fallback (cudaGetDeviceCount).");
+    }
+    Require(device >= 0 && device < device_count, "CUDA device ordinal out of range.");
+    SBNB_CUDA(cudaSetDevice(device));
+    engine->device = device;
+    cudaDeviceProp prop{};
+    SBNB_CUDA(cudaGetDeviceProperties(&prop, device));
+    engine->sm_count = prop.multiProcessorCount;
+    engine->taxon_count = taxon_count;
+    engine->pattern_count = pattern_count;
+    engine->range_begin = 0;
+    engine->range_end = pattern_count;
+    engine->categories = engine->spec.category_count;
+    engine->padded_categories = PadCategories(engine->categories);
+    engine->patterns_per_thread = EnvInt("SBNB_PATTERNS_PER_THREAD", 2);
+    if (engine->patterns_per_thread != 1 && engine->patterns_per_thread != 4)
+      engine->patterns_per_thread = 2;
+    SBNB_CUDA(cudaStreamCreateWithFlags(&engine->stream, cudaStreamNonBlocking));
+    // Tips padded with gap states (and weights with zeros) so the last tile
+    // needs no bounds checks: a tile is at most 128 * 4 patterns.
+    engine->tip_pitch = ((pattern_count + 511) / 512) * 512 + 512;
+    std::vector<uint8_t> tips(static_cast<size_t>(taxon_count) * engine->tip_pitch, 4);
+    for (int taxon = 0; taxon < taxon_count; taxon++)
+      for (int64_t k = 0; k < pattern_count; k++) {
+        const uint8_t s = tip_states[static_cast<size_t>(taxon) * pattern_count + k];
+        tips[static_cast<size_t>(taxon) * engine->tip_pitch + k] = s < 4 ? s : 4;
+      }
+    std::vector<double> weights(engine->tip_pitch, 0.0);
+    std::copy(pattern_weights, pattern_weights + pattern_count, weights.begin());
+    engine->tips.Upload(tips.data(), tips.size(), engine->stream);
+    engine->weights.Upload(weights.data(), weights.size(), engine->stream);
+    SBNB_CUDA(cudaStreamSynchronize(engine->stream));
+    *out = engine.release();
+  });
+}
+
+void sbnb_engine_destroy(sbnb_engine* engine) {
+  if (!engine) return;
+  cudaSetDevice(engine->device);
+  delete engine;
+}
+
+int32_t sbnb_engine_param_count(const sbnb_engine* engine) {
+  return engine ? engine->spec.param_count : -1;
+}
+
+int sbnb_engine_param_block(const sbnb_engine* engine, const char* key, int32_t* start,
+                            int32_t* length) {
+  return Guard([&] {
+    Require(engine && key && start && length, "NULL argument.");
+    const auto block = engine->spec.Block(key);
+    *start = block.first;
+    *length = block.second;
+  });
+}
+
+int32_t sbnb_engine_category_count(const sbnb_engine* engine) {
+  return engine ? engine->categories : -1;
+}
+
+int sbnb_log_likelihoods_unrooted(sbnb_engine* engine, const sbnb_tree_batch* trees,
+                                  const double* params, int32_t rescaling, double* out) {
+  return Guard([&] {
+    Require(engine != nullptr, "NULL engine.");
+    LogLikelihoods(engine, trees, params, rescaling != 0, false, false, out);
+  });
+}
+
+int sbnb_log_likelihoods_rooted(sbnb_engine* engine, const sbnb_tree_batch* trees,
+                                const double* params, int32_t rescaling, double* out) {
+  return Guard([&] {
+    Require(engine != nullptr, "NULL engine.");
+    LogLikelihoods(engine, trees, params, rescaling != 0, true, true, out);
+  });
+}
+
+int sbnb_unrooted_log_likelihoods_of_rooted(sbnb_engine* engine, const sbnb_tree_batch* trees,
+                                            const double* params, int32_t rescaling, double* out) {
+  return Guard([&] {
+    Require(engine != nullptr, "NULL engine.");
+    // fat_beagle.cpp:78-80: plain branch lengths, no rates, no Jacobian.
+    Require(trees && trees->node_count == 2 * engine->taxon_count - 1,
+            "Rooted trees must be bifurcating: node_count must be 2n-1.");
+    LogLikelihoods(engine, trees, params, rescaling != 0, false, false, out);
+  });
+}
+
+int sbnb_gradients_unrooted(sbnb_engine* engine, const sbnb_tree_batch* trees, const double* params,
+                            int32_t rescaling, const sbnb_gradient_out* out) {
+  return Guard([&] {
+    Require(engine != nullptr, "NULL engine.");
+    Gradients(engine, trees, params, rescaling != 0, false, out);
+  });
+}
+
+int sbnb_gradients_rooted(sbnb_engine* engine, const sbnb_tree_batch* trees, const double* params,
+                          int32_t rescaling, const sbnb_gradient_out* out) {
+  return Guard([&] {
+    Require(engine != nullptr, "NULL engine.");
+    Gradients(engine, trees, params, rescaling != 0, true, out);
+  });
+}
+
+int sbnb_batch_stage(sbnb_engine* engine, const sbnb_tree_batch* trees, const double* params,
+                     int32_t stage_flags, sbnb_batch** out) {
+  return Guard([&] {
+    Require(engine && out, "NULL argument.");
+    *out = nullptr;
+    *out = Stage(engine, trees, params, (stage_flags & SBNB_STAGE_ROOTED) != 0,
+                 (stage_flags & SBNB_STAGE_SUBSTITUTION_FD) != 0)
+               .release();
+  });
+}
+
+int sbnb_batch_run(sbnb_engine* engine, sbnb_batch* batch, int32_t mode, int32_t rescaling) {
+  return Guard([&] {
+    Require(engine && batch, "NULL argument.");
+    Run(engine, batch, mode, rescaling != 0);
+  });
+}
+
+int sbnb_batch_fetch(sbnb_engine* engine, sbnb_batch* batch, double* log_likelihoods,
+                     double* branch_gradients, double* rate_gradients) {
+  return Guard([&] {
+    Require(engine && batch, "NULL argument.");
+    Fetch(engine, batch, log_likelihoods, branch_gradients, rate_gradients);
+  });
+}
+
+void sbnb_batch_destroy(sbnb_engine* engine, sbnb_batch* batch) {
+  if (engine) cudaSetDevice(engine->device);
+  delete batch;
+}
+
+int32_t sbnb_batch_evaluation_count(const sbnb_batch* batch) {
+  if (!batch) return -1;
+  return batch->last_mode == SBNB_MODE_BRANCH_GRADIENT ? batch->vtree_count : batch->tree_count;
+}
+
+void* sbnb_engine_stream(sbnb_engine* engine) { return engine ? engine->stream : nullptr; }
+
+int64_t sbnb_engine_launch_count(const sbnb_engine* engine) {
+  return engine ? engine->launch_count : -1;
+}
+
+double sbnb_batch_algorithmic_bytes(const sbnb_batch* batch, int32_t mode) {
+  // U = 32 C P bytes per partial; (2n-2) U per log-likelihood,
+  // (10n-14) U per log-likelihood + branch gradient.
+  if (!batch) return 0.0;
+  const double n = batch->taxon_count;
+  const double units = (mode == SBNB_MODE_BRANCH_GRADIENT) ? (10.0 * n - 14.0) : (2.0 * n - 2.0);
+  return units * 32.0 * batch->categories * static_cast<double>(batch->patterns) * batch->tree_count;
+}
+
+int sbnb_engine_set_pattern_range(sbnb_engine* engine, int64_t begin, int64_t end) {
+  return Guard([&] {
+    Require(engine != nullptr, "NULL engine.");
+    Require(0 <= begin && begin < end && end <= engine->pattern_count,
+            "Pattern range must satisfy 0 <= begin < end <= pattern_count.");
+    engine->range_begin = begin;
+    engine->range_end = end;
+  });
+}
+
+}  // extern "C"
