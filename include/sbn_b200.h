@@ -176,6 +176,26 @@ double sbnb_batch_algorithmic_bytes(const sbnb_batch* batch, int32_t mode);
  * sum-all-reduces log-likelihoods and edge derivatives). */
 int sbnb_engine_set_pattern_range(sbnb_engine* engine, int64_t begin, int64_t end);
 
+/* ---- host-only diagnostics (no device needed; used by the CPU test-suite) -- */
+
+/* The traversal programs generated for one topology.  post_ops / pre_ops
+ * receive (taxon_count-1) records of 8 int32 each:
+ *   post: {node, child0, child1, dst_slot, child0_slot, child1_slot, flags, 0}
+ *   pre:  {node, child0, child1, pre_slot, child0_dst_slot, child1_dst_slot, flags, 0}
+ * flags: 1 = child0 is a leaf, 2 = child1 is a leaf, 4 = node is the root.
+ * slots[0..1] = stack depth of the post-order / pre-order walk. */
+int sbnb_debug_tree_program(const int32_t* parent_ids, int32_t node_count, int32_t taxon_count,
+                            int32_t* post_ops, int32_t* pre_ops, int32_t* slots);
+
+/* The model tables built from one parameter row: eigenvectors[16],
+ * inverse_eigenvectors[16], eigenvalues[4], frequencies[4], q[16] (row-major),
+ * then category rates / weights / rate derivatives (category_count each). */
+int sbnb_debug_model_tables(const char* substitution, const char* site, const char* clock,
+                            const double* param_row, double* eigenvectors,
+                            double* inverse_eigenvectors, double* eigenvalues, double* frequencies,
+                            double* q, double* category_rates, double* category_weights,
+                            double* category_rate_derivatives);
+
 #ifdef __cplusplus
 }
 #endif

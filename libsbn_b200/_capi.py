@@ -78,6 +78,9 @@ SIGNATURES = {
     "sbnb_engine_launch_count": (_c.c_int64, [_c.c_void_p]),
     "sbnb_batch_algorithmic_bytes": (_c.c_double, [_c.c_void_p, _c.c_int32]),
     "sbnb_engine_set_pattern_range": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int64]),
+    "sbnb_debug_tree_program": (_c.c_int, [_P(_c.c_int32), _c.c_int32, _c.c_int32, _P(_c.c_int32),
+                                           _P(_c.c_int32), _P(_c.c_int32)]),
+    "sbnb_debug_model_tables": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p] + [_P(_c.c_double)] * 9),
 }
 
 MODE_LOG_LIKELIHOOD = 0

@@ -803,4 +803,40 @@ int sbnb_engine_set_pattern_range(sbnb_engine* engine, int64_t begin, int64_t en
   });
 }
 
+int sbnb_debug_tree_program(const int32_t* parent_ids, int32_t node_count, int32_t taxon_count,
+                            int32_t* post_ops, int32_t* pre_ops, int32_t* slots) {
+  return Guard([&] {
+    Require(parent_ids && post_ops && pre_ops && slots, "NULL argument.");
+    const TreeProgram program = BuildTreeProgram(parent_ids, node_count, taxon_count);
+    static_assert(sizeof(PostOp) == 32 && sizeof(PreOp) == 32, "ops are 8 x int32");
+    std::memcpy(post_ops, program.post.data(), program.post.size() * sizeof(PostOp));
+    std::memcpy(pre_ops, program.pre.data(), program.pre.size() * sizeof(PreOp));
+    slots[0] = program.post_slots;
+    slots[1] = program.pre_slots;
+  });
+}
+
+int sbnb_debug_model_tables(const char* substitution, const char* site, const char* clock,
+                            const double* param_row, double* eigenvectors,
+                            double* inverse_eigenvectors, double* eigenvalues, double* frequencies,
+                            double* q, double* category_rates, double* category_weights,
+                            double* category_rate_derivatives) {
+  return Guard([&] {
+    Require(substitution && site && clock, "NULL model specification string.");
+    const ModelSpec spec = ModelSpec::Parse(substitution, site, clock);
+    Require(spec.param_count == 0 || param_row != nullptr, "NULL parameter row.");
+    ModelTables tables;
+    BuildModelTables(spec, param_row, &tables);
+    if (eigenvectors) std::copy(tables.evec, tables.evec + 16, eigenvectors);
+    if (inverse_eigenvectors) std::copy(tables.ivec, tables.ivec + 16, inverse_eigenvectors);
+    if (eigenvalues) std::copy(tables.eval, tables.eval + 4, eigenvalues);
+    if (frequencies) std::copy(tables.freqs, tables.freqs + 4, frequencies);
+    if (q) std::copy(tables.q, tables.q + 16, q);
+    const int C = spec.category_count;
+    if (category_rates) std::copy(tables.rates, tables.rates + C, category_rates);
+    if (category_weights) std::copy(tables.weights, tables.weights + C, category_weights);
+    if (category_rate_derivatives) std::copy(tables.drates, tables.drates + C, category_rate_derivatives);
+  });
+}
+
 }  // extern "C"
