@@ -169,6 +169,16 @@ int32_t sbnb_batch_evaluation_count(const sbnb_batch* batch);
 void* sbnb_engine_stream(sbnb_engine* engine);
 int64_t sbnb_engine_launch_count(const sbnb_engine* engine);
 double sbnb_batch_algorithmic_bytes(const sbnb_batch* batch, int32_t mode);
+/* Cumulative bytes this engine has copied host->device and device->host
+ * (staging goes through a page-locked arena, so these are DMA transfers). */
+int sbnb_engine_transfer_bytes(const sbnb_engine* engine, int64_t* host_to_device,
+                               int64_t* device_to_host);
+/* Device time of the tree-walk kernel (the dominant kernel), measured with
+ * CUDA events on the engine's stream around each launch made by
+ * sbnb_batch_run: cumulative milliseconds and number of launches timed since
+ * the last reset.  Waits for outstanding launches. */
+int sbnb_engine_walk_timing(sbnb_engine* engine, double* total_ms, int64_t* samples,
+                            int32_t reset);
 
 /* Restrict this engine to the pattern range [begin, end) of the alignment it
  * was created with (site-pattern sharding across GPUs: every rank stages the

@@ -77,6 +77,8 @@ SIGNATURES = {
     "sbnb_engine_stream": (_c.c_void_p, [_c.c_void_p]),
     "sbnb_engine_launch_count": (_c.c_int64, [_c.c_void_p]),
     "sbnb_batch_algorithmic_bytes": (_c.c_double, [_c.c_void_p, _c.c_int32]),
+    "sbnb_engine_transfer_bytes": (_c.c_int, [_c.c_void_p, _P(_c.c_int64), _P(_c.c_int64)]),
+    "sbnb_engine_walk_timing": (_c.c_int, [_c.c_void_p, _P(_c.c_double), _P(_c.c_int64), _c.c_int32]),
     "sbnb_engine_set_pattern_range": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int64]),
     "sbnb_debug_tree_program": (_c.c_int, [_P(_c.c_int32), _c.c_int32, _c.c_int32, _P(_c.c_int32),
                                            _P(_c.c_int32), _P(_c.c_int32)]),

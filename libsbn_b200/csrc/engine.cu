@@ -57,9 +57,11 @@ class DeviceArray {
     SBNB_CUDA(cudaMalloc(&ptr_, std::max<size_t>(count, 1) * sizeof(T)));
     capacity_ = count;
   }
-  void Upload(const T* host, size_t count, cudaStream_t stream) {
+  // Returns the number of bytes copied host -> device.
+  size_t Upload(const T* host, size_t count, cudaStream_t stream) {
     Reserve(count);
     if (count) SBNB_CUDA(cudaMemcpyAsync(ptr_, host, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return count * sizeof(T);
   }
   T* get() const { return ptr_; }
   size_t capacity() const { return capacity_; }
@@ -67,6 +69,38 @@ class DeviceArray {
  private:
   T* ptr_ = nullptr;
   size_t capacity_ = 0;
+};
+
+// Page-locked host staging area (grows on demand, reused between calls) so that
+// the host -> device copies of a staged batch are real asynchronous DMA.
+class PinnedArena {
+ public:
+  PinnedArena() = default;
+  PinnedArena(const PinnedArena&) = delete;
+  PinnedArena& operator=(const PinnedArena&) = delete;
+  ~PinnedArena() { cudaFreeHost(base_); }
+  void Reset(size_t bytes) {
+    if (bytes > capacity_) {
+      cudaFreeHost(base_);
+      base_ = nullptr;
+      capacity_ = 0;
+      SBNB_CUDA(cudaMallocHost(&base_, bytes));
+      capacity_ = bytes;
+    }
+    used_ = 0;
+  }
+  template <typename T>
+  T* Take(size_t count) {
+    used_ = (used_ + 255) / 256 * 256;
+    T* out = reinterpret_cast<T*>(static_cast<char*>(base_) + used_);
+    used_ += count * sizeof(T);
+    if (used_ > capacity_) Fail(SBNB_ERR_OUT_OF_MEMORY, "pinned staging arena overflow");
+    return out;
+  }
+
+ private:
+  void* base_ = nullptr;
+  size_t capacity_ = 0, used_ = 0;
 };
 
 int PadCategories(int c) {
@@ -100,12 +134,26 @@ struct sbnb_engine {
   int padded_categories = 1;  // power of two >= C (extra categories have weight 0)
   int patterns_per_thread = 2;
   cudaStream_t stream = nullptr;
+  // CUDA-event pairs bracketing the base tree-walk launch of the last
+  // kWalkRing runs; harvested into (walk_total_ms, walk_samples).
+  static constexpr int kWalkRing = 32;
+  cudaEvent_t walk_begin[kWalkRing] = {}, walk_end[kWalkRing] = {};
+  bool walk_pending[kWalkRing] = {};
+  int64_t walk_runs = 0;
+  double walk_total_ms = 0.0, walk_last_ms = 0.0;
+  int64_t walk_samples = 0;
   int64_t launch_count = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;
+  PinnedArena staging;
   DeviceArray<uint8_t> tips;
   DeviceArray<double> weights;
   DeviceArray<double2> scratch;  // post-order partial arena, reused by every gradient run
 
   ~sbnb_engine() {
+    for (int i = 0; i < kWalkRing; i++) {
+      if (walk_begin[i]) cudaEventDestroy(walk_begin[i]);
+      if (walk_end[i]) cudaEventDestroy(walk_end[i]);
+    }
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -299,17 +347,27 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
   batch->vtree_count = T * (1 + fd_evals);
   if (T == 0) return batch;
 
+  // Everything that goes to the device is assembled in page-locked memory.
+  const size_t op_count = static_cast<size_t>(T) * (n - 1);
+  const size_t max_models = static_cast<size_t>(T) * (1 + fd_evals);
+  e->staging.Reset(op_count * (sizeof(PostOp) + sizeof(PreOp)) + 3 * batch->vtree_count * sizeof(int32_t) +
+                   max_models * sizeof(ModelTables) + static_cast<size_t>(T) * N * sizeof(double) + 16 * 256);
+  PostOp* post = e->staging.Take<PostOp>(op_count);
+  PreOp* pre = e->staging.Take<PreOp>(op_count);
+  int32_t* vtree_program = e->staging.Take<int32_t>(batch->vtree_count);
+  int32_t* vtree_model = e->staging.Take<int32_t>(batch->vtree_count);
+  int32_t* vtree_lengths = e->staging.Take<int32_t>(batch->vtree_count);
+  ModelTables* models = e->staging.Take<ModelTables>(max_models);
+  double* lengths = e->staging.Take<double>(static_cast<size_t>(T) * N);
+
   // Programs + branch lengths.
   batch->programs.reserve(T);
-  batch->lengths.assign(static_cast<size_t>(T) * N, 0.0);
-  std::vector<PostOp> post(static_cast<size_t>(T) * (n - 1));
-  std::vector<PreOp> pre(static_cast<size_t>(T) * (n - 1));
   int slots = 1;
   for (int t = 0; t < T; t++) {
     TreeProgram program = BuildTreeProgram(
         trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1), trees->node_count, n);
     const double* in = trees->branch_lengths + static_cast<size_t>(t) * trees->node_count;
-    double* out = batch->lengths.data() + static_cast<size_t>(t) * N;
+    double* out = lengths + static_cast<size_t>(t) * N;
     std::copy(in, in + trees->node_count, out);
     if (program.was_trifurcating) {
       // Detrifurcate (unrooted_tree.cpp:31-35): the node that takes the old
@@ -322,17 +380,20 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
       const double* rates = trees->rates + static_cast<size_t>(t) * (N - 1);
       for (int i = 0; i < N - 1; i++) out[i] *= rates[i];
     }
-    std::copy(program.post.begin(), program.post.end(), post.begin() + static_cast<size_t>(t) * (n - 1));
-    std::copy(program.pre.begin(), program.pre.end(), pre.begin() + static_cast<size_t>(t) * (n - 1));
+    std::copy(program.post.begin(), program.post.end(), post + static_cast<size_t>(t) * (n - 1));
+    std::copy(program.pre.begin(), program.pre.end(), pre + static_cast<size_t>(t) * (n - 1));
     slots = std::max({slots, program.post_slots, program.pre_slots});
+    program.post.clear();
+    program.post.shrink_to_fit();
+    program.pre.clear();
+    program.pre.shrink_to_fit();
     batch->programs.push_back(std::move(program));
   }
   batch->slots = slots;
+  batch->lengths.assign(lengths, lengths + static_cast<size_t>(T) * N);
 
   // Models: one table per distinct consecutive parameter row (+ its FD rows).
-  std::vector<ModelTables> models;
-  std::vector<int32_t> vtree_program(batch->vtree_count), vtree_model(batch->vtree_count),
-      vtree_lengths(batch->vtree_count);
+  size_t model_count = 0;
   const int K = spec.param_count;
   int previous_base_model = -1;
   std::vector<std::vector<double>> fd_rows;
@@ -341,15 +402,11 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
     const bool same_as_previous =
         t > 0 && (K == 0 || std::memcmp(row, row - K, sizeof(double) * K) == 0);
     if (!same_as_previous) {
-      previous_base_model = static_cast<int>(models.size());
-      models.emplace_back();
-      BuildModelTables(spec, row, &models.back());
+      previous_base_model = static_cast<int>(model_count);
+      BuildModelTables(spec, row, &models[model_count++]);
       if (fd_evals) {
         FiniteDifferenceRows(spec, row, kFiniteDifferenceDelta, &fd_rows);
-        for (const auto& fd_row : fd_rows) {
-          models.emplace_back();
-          BuildModelTables(spec, fd_row.data(), &models.back());
-        }
+        for (const auto& fd_row : fd_rows) BuildModelTables(spec, fd_row.data(), &models[model_count++]);
       }
     }
     vtree_program[t] = t;
@@ -364,20 +421,32 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
   }
 
   cudaStream_t s = e->stream;
-  batch->post_ops.Upload(post.data(), post.size(), s);
-  batch->pre_ops.Upload(pre.data(), pre.size(), s);
-  batch->vtree_program.Upload(vtree_program.data(), vtree_program.size(), s);
-  batch->vtree_model.Upload(vtree_model.data(), vtree_model.size(), s);
-  batch->vtree_lengths.Upload(vtree_lengths.data(), vtree_lengths.size(), s);
-  batch->models.Upload(models.data(), models.size(), s);
-  batch->d_lengths.Upload(batch->lengths.data(), batch->lengths.size(), s);
+  e->h2d_bytes += batch->post_ops.Upload(post, op_count, s);
+  e->h2d_bytes += batch->pre_ops.Upload(pre, op_count, s);
+  e->h2d_bytes += batch->vtree_program.Upload(vtree_program, batch->vtree_count, s);
+  e->h2d_bytes += batch->vtree_model.Upload(vtree_model, batch->vtree_count, s);
+  e->h2d_bytes += batch->vtree_lengths.Upload(vtree_lengths, batch->vtree_count, s);
+  e->h2d_bytes += batch->models.Upload(models, model_count, s);
+  e->h2d_bytes += batch->d_lengths.Upload(lengths, static_cast<size_t>(T) * N, s);
   batch->matrices.Reserve(static_cast<size_t>(batch->vtree_count) * (N - 1) * e->padded_categories * 16);
   batch->logl.Reserve(batch->vtree_count);
   batch->grad.Reserve(static_cast<size_t>(T) * N);
   batch->rgrad.Reserve(static_cast<size_t>(T) * N);
-  // The uploads read pageable host vectors that die with this scope.
+  // The staging arena is reused by the next call.
   SBNB_CUDA(cudaStreamSynchronize(s));
   return batch;
+}
+
+// Folds one finished event pair into the running totals (waits for it).
+void HarvestWalkTiming(sbnb_engine* e, int ring) {
+  if (!e->walk_pending[ring]) return;
+  SBNB_CUDA(cudaEventSynchronize(e->walk_end[ring]));
+  float ms = 0.f;
+  SBNB_CUDA(cudaEventElapsedTime(&ms, e->walk_begin[ring], e->walk_end[ring]));
+  e->walk_total_ms += ms;
+  e->walk_last_ms = ms;
+  e->walk_samples++;
+  e->walk_pending[ring] = false;
 }
 
 WalkParams BaseParams(sbnb_engine* e, sbnb_batch* b) {
@@ -456,7 +525,12 @@ void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
   p.logl_partial = b->logl_partial.get();
   p.grad_partial = b->grad_partial.get();
   p.rgrad_partial = b->rgrad_partial.get();
+  const int ring = static_cast<int>(e->walk_runs++ % sbnb_engine::kWalkRing);
+  HarvestWalkTiming(e, ring);  // the slot about to be reused
+  SBNB_CUDA(cudaEventRecord(e->walk_begin[ring], s));
   Dispatch(e, p, grad, rescaling, /*launch=*/true, chunks);
+  SBNB_CUDA(cudaEventRecord(e->walk_end[ring], s));
+  e->walk_pending[ring] = true;
   if (fd_vtrees > 0) {
     WalkParams q = p;
     q.vtree_begin = T;
@@ -496,18 +570,22 @@ void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rg
   const size_t per_tree = static_cast<size_t>(b->node_count);
   cudaStream_t s = e->stream;
   if (b->tree_count > 0) {
-    if (logl)
+    if (logl) {
       SBNB_CUDA(cudaMemcpyAsync(logl, b->logl.get(), vtrees * sizeof(double), cudaMemcpyDeviceToHost, s));
+      e->d2h_bytes += vtrees * sizeof(double);
+    }
     if (grad) {
       Require(was_grad, "No gradient available: the last run was a log-likelihood run.");
       SBNB_CUDA(cudaMemcpyAsync(grad, b->grad.get(), b->tree_count * per_tree * sizeof(double),
                                 cudaMemcpyDeviceToHost, s));
+      e->d2h_bytes += b->tree_count * per_tree * sizeof(double);
     }
     if (rgrad) {
       Require(was_grad, "No gradient available: the last run was a log-likelihood run.");
       if (e->padded_categories > 1) {
         SBNB_CUDA(cudaMemcpyAsync(rgrad, b->rgrad.get(), b->tree_count * per_tree * sizeof(double),
                                   cudaMemcpyDeviceToHost, s));
+        e->d2h_bytes += b->tree_count * per_tree * sizeof(double);
       } else {
         std::fill(rgrad, rgrad + b->tree_count * per_tree, 0.0);
       }
@@ -657,6 +735,10 @@ int sbnb_engine_create(const char* substitution, const char* site, const char* c
     if (engine->patterns_per_thread != 1 && engine->patterns_per_thread != 4)
       engine->patterns_per_thread = 2;
     SBNB_CUDA(cudaStreamCreateWithFlags(&engine->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < sbnb_engine::kWalkRing; i++) {
+      SBNB_CUDA(cudaEventCreate(&engine->walk_begin[i]));
+      SBNB_CUDA(cudaEventCreate(&engine->walk_end[i]));
+    }
     // Tips padded with gap states (and weights with zeros) so the last tile
     // needs no bounds checks: a tile is at most 128 * 4 patterns.
     engine->tip_pitch = ((pattern_count + 511) / 512) * 512 + 512;
@@ -782,6 +864,32 @@ void* sbnb_engine_stream(sbnb_engine* engine) { return engine ? engine->stream :
 
 int64_t sbnb_engine_launch_count(const sbnb_engine* engine) {
   return engine ? engine->launch_count : -1;
+}
+
+int sbnb_engine_transfer_bytes(const sbnb_engine* engine, int64_t* host_to_device,
+                               int64_t* device_to_host) {
+  return Guard([&] {
+    Require(engine && host_to_device && device_to_host, "NULL argument.");
+    *host_to_device = engine->h2d_bytes;
+    *device_to_host = engine->d2h_bytes;
+  });
+}
+
+int sbnb_engine_walk_timing(sbnb_engine* engine, double* total_ms, int64_t* samples,
+                            int32_t reset) {
+  return Guard([&] {
+    Require(engine && total_ms && samples, "NULL argument.");
+    SBNB_CUDA(cudaSetDevice(engine->device));
+    // oldest first, so that walk_last_ms ends up being the newest run
+    for (int i = 0; i < sbnb_engine::kWalkRing; i++)
+      HarvestWalkTiming(engine, static_cast<int>((engine->walk_runs + i) % sbnb_engine::kWalkRing));
+    *total_ms = engine->walk_total_ms;
+    *samples = engine->walk_samples;
+    if (reset) {
+      engine->walk_total_ms = 0.0;
+      engine->walk_samples = 0;
+    }
+  });
 }
 
 double sbnb_batch_algorithmic_bytes(const sbnb_batch* batch, int32_t mode) {

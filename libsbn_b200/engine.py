@@ -209,13 +209,14 @@ class Engine:
             _capi.as_double_ptr(out)))
         return out
 
-    def gradients(self, trees, params=None, rescaling=False, rooted=False):
-        """Engine::Gradients: one PhyloGradient per tree."""
+    def gradients(self, trees, params=None, rescaling=False, rooted=False, substitution_gradient=True):
+        """Engine::Gradients: one PhyloGradient per tree.  substitution_gradient=False
+        skips the 16 finite-difference log-likelihood sweeps of a GTR model."""
         lib = _capi.load()
         T, n = trees.tree_count, self.taxon_count
         params = self._params(params, T)
         spec = self.specification
-        fd_size = {"GTR": 8, "HKY": 4}.get(spec.substitution, 0)
+        fd_size = {"GTR": 8, "HKY": 4}.get(spec.substitution, 0) if substitution_gradient else 0
         buffers = {"log_likelihood": np.zeros(T)}
         if rooted:
             buffers["ratios_root_height"] = np.zeros((T, n - 1))
@@ -255,6 +256,21 @@ class Engine:
     @property
     def stream(self):
         return _capi.load().sbnb_engine_stream(self._handle)
+
+    @property
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes copied so far."""
+        h2d, d2h = ctypes.c_int64(), ctypes.c_int64()
+        _capi.check(_capi.load().sbnb_engine_transfer_bytes(self._handle, ctypes.byref(h2d), ctypes.byref(d2h)))
+        return h2d.value, d2h.value
+
+    def walk_timing(self, reset=False):
+        """(total ms, launches) of the tree-walk kernel since the last reset,
+        from CUDA events around each launch; waits for outstanding launches."""
+        total, samples = ctypes.c_double(), ctypes.c_int64()
+        _capi.check(_capi.load().sbnb_engine_walk_timing(self._handle, ctypes.byref(total),
+                                                         ctypes.byref(samples), int(reset)))
+        return total.value, samples.value
 
     @property
     def launch_count(self):
