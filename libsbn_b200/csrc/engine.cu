@@ -173,8 +173,7 @@ struct sbnb_batch {
   std::vector<TreeProgram> programs;
   std::vector<double> lengths;  // [T][2n-1] after detrifurcation / rate scaling / root slide
   // device side
-  DeviceArray<PostOp> post_ops;
-  DeviceArray<PreOp> pre_ops;
+  DeviceArray<WalkOp> ops;  // [tree][2(n-1)]: post-order ops then pre-order ops
   DeviceArray<int32_t> vtree_program, vtree_model, vtree_lengths;
   DeviceArray<ModelTables> models;
   DeviceArray<double> d_lengths, matrices;
@@ -194,7 +193,7 @@ struct LaunchPlan {
 template <int C, int K, bool GRAD, bool RESCALE>
 LaunchPlan PlanAndLaunch(sbnb_engine* e, WalkParams p, bool launch, int chunks_override) {
   auto kernel = TreeWalkKernel<C, K, GRAD, RESCALE>;
-  const size_t smem = static_cast<size_t>(p.slots) * K * kThreads * (sizeof(double2) * 2 + sizeof(int));
+  const size_t smem = WalkSmemBytes(p.slots, C, K, GRAD, RESCALE);
   if (smem > 227 * 1024)
     Fail(SBNB_ERR_INVALID_ARGUMENT, "Tree too deep for the shared-memory stack: " +
                                         std::to_string(p.slots) + " slots.");
@@ -348,12 +347,11 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
   if (T == 0) return batch;
 
   // Everything that goes to the device is assembled in page-locked memory.
-  const size_t op_count = static_cast<size_t>(T) * (n - 1);
+  const size_t op_count = static_cast<size_t>(T) * 2 * (n - 1);
   const size_t max_models = static_cast<size_t>(T) * (1 + fd_evals);
-  e->staging.Reset(op_count * (sizeof(PostOp) + sizeof(PreOp)) + 3 * batch->vtree_count * sizeof(int32_t) +
+  e->staging.Reset(op_count * sizeof(WalkOp) + 3 * batch->vtree_count * sizeof(int32_t) +
                    max_models * sizeof(ModelTables) + static_cast<size_t>(T) * N * sizeof(double) + 16 * 256);
-  PostOp* post = e->staging.Take<PostOp>(op_count);
-  PreOp* pre = e->staging.Take<PreOp>(op_count);
+  WalkOp* ops = e->staging.Take<WalkOp>(op_count);
   int32_t* vtree_program = e->staging.Take<int32_t>(batch->vtree_count);
   int32_t* vtree_model = e->staging.Take<int32_t>(batch->vtree_count);
   int32_t* vtree_lengths = e->staging.Take<int32_t>(batch->vtree_count);
@@ -380,8 +378,19 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
       const double* rates = trees->rates + static_cast<size_t>(t) * (N - 1);
       for (int i = 0; i < N - 1; i++) out[i] *= rates[i];
     }
-    std::copy(program.post.begin(), program.post.end(), post + static_cast<size_t>(t) * (n - 1));
-    std::copy(program.pre.begin(), program.pre.end(), pre + static_cast<size_t>(t) * (n - 1));
+    // Pack both programs into the 16-byte records the kernel streams.
+    auto slot_byte = [](int32_t slot) { return slot < 0 ? 0xff : (slot & 0xff); };
+    Require(program.post_slots < 255 && program.pre_slots < 255 && N < (1 << 24), "Tree too large.");
+    WalkOp* tree_ops = ops + static_cast<size_t>(t) * 2 * (n - 1);
+    for (int o = 0; o < n - 1; o++) {
+      const PostOp& op = program.post[o];
+      tree_ops[o] = make_int4(op.a, op.b, op.node | (op.flags << 24),
+                              slot_byte(op.dst_slot) | (slot_byte(op.a_slot) << 8) | (slot_byte(op.b_slot) << 16));
+      const PreOp& pre = program.pre[o];
+      tree_ops[n - 1 + o] =
+          make_int4(pre.a, pre.b, pre.node | (pre.flags << 24),
+                    slot_byte(pre.pre_slot) | (slot_byte(pre.a_dst_slot) << 8) | (slot_byte(pre.b_dst_slot) << 16));
+    }
     slots = std::max({slots, program.post_slots, program.pre_slots});
     program.post.clear();
     program.post.shrink_to_fit();
@@ -421,14 +430,14 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
   }
 
   cudaStream_t s = e->stream;
-  e->h2d_bytes += batch->post_ops.Upload(post, op_count, s);
-  e->h2d_bytes += batch->pre_ops.Upload(pre, op_count, s);
+  e->h2d_bytes += batch->ops.Upload(ops, op_count, s);
   e->h2d_bytes += batch->vtree_program.Upload(vtree_program, batch->vtree_count, s);
   e->h2d_bytes += batch->vtree_model.Upload(vtree_model, batch->vtree_count, s);
   e->h2d_bytes += batch->vtree_lengths.Upload(vtree_lengths, batch->vtree_count, s);
   e->h2d_bytes += batch->models.Upload(models, model_count, s);
   e->h2d_bytes += batch->d_lengths.Upload(lengths, static_cast<size_t>(T) * N, s);
-  batch->matrices.Reserve(static_cast<size_t>(batch->vtree_count) * (N - 1) * e->padded_categories * 16);
+  batch->matrices.Reserve(static_cast<size_t>(batch->vtree_count) * (N - 1) * e->padded_categories *
+                          kMatrixDoubles);
   batch->logl.Reserve(batch->vtree_count);
   batch->grad.Reserve(static_cast<size_t>(T) * N);
   batch->rgrad.Reserve(static_cast<size_t>(T) * N);
@@ -457,8 +466,7 @@ WalkParams BaseParams(sbnb_engine* e, sbnb_batch* b) {
   p.pattern_begin = e->range_begin;
   p.pattern_end = e->range_end;
   p.taxon_count = e->taxon_count;
-  p.post_ops = b->post_ops.get();
-  p.pre_ops = b->pre_ops.get();
+  p.ops = b->ops.get();
   p.vtree_program = b->vtree_program.get();
   p.vtree_model = b->vtree_model.get();
   p.models = b->models.get();
