@@ -103,10 +103,12 @@ class PinnedArena {
   size_t capacity_ = 0, used_ = 0;
 };
 
+// Category counts the tree walk is instantiated for; other counts run padded
+// with zero-weight categories.
 int PadCategories(int c) {
-  int padded = 1;
-  while (padded < c) padded <<= 1;
-  return padded;
+  for (int supported : {1, 2, 3, 4, 8, 16})
+    if (c <= supported) return supported;
+  return 0;
 }
 
 int EnvInt(const char* name, int fallback) {
@@ -131,8 +133,10 @@ struct sbnb_engine {
   int64_t tip_pitch = 0;
   int64_t range_begin = 0, range_end = 0;
   int categories = 1;         // C
-  int padded_categories = 1;  // power of two >= C (extra categories have weight 0)
+  int padded_categories = 1;  // instantiated count >= C (extra categories have weight 0)
   int patterns_per_thread = 2;
+  std::vector<uint8_t> host_tips;    // [taxon][pattern], states clamped to 0..4
+  std::vector<double> host_weights;  // [pattern]
   cudaStream_t stream = nullptr;
   // CUDA-event pairs bracketing the base tree-walk launch of the last
   // kWalkRing runs; harvested into (walk_total_ms, walk_samples).
@@ -147,7 +151,9 @@ struct sbnb_engine {
   PinnedArena staging;
   DeviceArray<uint8_t> tips;
   DeviceArray<double> weights;
-  DeviceArray<double2> scratch;  // post-order partial arena, reused by every gradient run
+  DeviceArray<double2> scratch;  // evolved post-order partial arena, reused by every gradient run
+  DeviceArray<double2> stack;    // per-CTA partial stacks
+  DeviceArray<int32_t> stack_exps;
 
   ~sbnb_engine() {
     for (int i = 0; i < kWalkRing; i++) {
@@ -193,17 +199,14 @@ struct LaunchPlan {
 template <int C, int K, bool GRAD, bool RESCALE>
 LaunchPlan PlanAndLaunch(sbnb_engine* e, WalkParams p, bool launch, int chunks_override) {
   auto kernel = TreeWalkKernel<C, K, GRAD, RESCALE>;
-  const size_t smem = WalkSmemBytes(p.slots, C, K, GRAD, RESCALE);
-  if (smem > 227 * 1024)
-    Fail(SBNB_ERR_INVALID_ARGUMENT, "Tree too deep for the shared-memory stack: " +
-                                        std::to_string(p.slots) + " slots.");
+  const size_t smem = WalkSmemBytes(C, K);
   SBNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   int per_sm = 0;
   SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
   if (per_sm < 1) Fail(SBNB_ERR_CUDA, "TreeWalkKernel does not fit on an SM.");
   const int resident = per_sm * e->sm_count;
-  constexpr int kTilePatterns = (kThreads / C) * K;
+  constexpr int kTilePatterns = kThreads * K;
   LaunchPlan plan;
   const int64_t patterns = p.pattern_end - p.pattern_begin;
   plan.tiles_total = static_cast<int>((patterns + kTilePatterns - 1) / kTilePatterns);
@@ -224,6 +227,19 @@ LaunchPlan PlanAndLaunch(sbnb_engine* e, WalkParams p, bool launch, int chunks_o
     p.tiles_total = plan.tiles_total;
     p.tiles_per_chunk = plan.tiles_per_chunk;
     p.chunks = plan.chunks;
+    // Per-CTA arenas: the partial stack and (gradient runs) the scratch arena.
+    const size_t block = static_cast<size_t>(K) * C * 2 * kThreads;  // double2 per partial block
+    const size_t slots = static_cast<size_t>(std::max(p.slots, 1));
+    e->stack.Reserve(static_cast<size_t>(plan.grid) * slots * block);
+    p.stack = e->stack.get();
+    if (RESCALE) {
+      e->stack_exps.Reserve(static_cast<size_t>(plan.grid) * slots * K * kThreads);
+      p.stack_exps = e->stack_exps.get();
+    }
+    if (GRAD) {
+      e->scratch.Reserve(static_cast<size_t>(plan.grid) * (p.taxon_count - 1) * block);
+      p.scratch = e->scratch.get();
+    }
     kernel<<<plan.grid, kThreads, smem, e->stream>>>(p);
     SBNB_CUDA(cudaGetLastError());
     e->launch_count++;
@@ -245,14 +261,8 @@ LaunchPlan DispatchModes(sbnb_engine* e, const WalkParams& p, bool grad, bool re
 template <int C>
 LaunchPlan DispatchK(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
                      int chunks_override) {
-  switch (e->patterns_per_thread) {
-    case 1:
-      return DispatchModes<C, 1>(e, p, grad, rescale, launch, chunks_override);
-    case 4:
-      return DispatchModes<C, 4>(e, p, grad, rescale, launch, chunks_override);
-    default:
-      return DispatchModes<C, 2>(e, p, grad, rescale, launch, chunks_override);
-  }
+  if (e->patterns_per_thread == 1) return DispatchModes<C, 1>(e, p, grad, rescale, launch, chunks_override);
+  return DispatchModes<C, 2>(e, p, grad, rescale, launch, chunks_override);
 }
 
 LaunchPlan Dispatch(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
@@ -262,14 +272,38 @@ LaunchPlan Dispatch(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale
       return DispatchK<1>(e, p, grad, rescale, launch, chunks_override);
     case 2:
       return DispatchK<2>(e, p, grad, rescale, launch, chunks_override);
+    case 3:
+      return DispatchK<3>(e, p, grad, rescale, launch, chunks_override);
     case 4:
       return DispatchK<4>(e, p, grad, rescale, launch, chunks_override);
-    case 8:
-      return DispatchK<8>(e, p, grad, rescale, launch, chunks_override);
+    case 8:  // a thread holds all categories of its patterns in registers: one pattern each
+      return DispatchModes<8, 1>(e, p, grad, rescale, launch, chunks_override);
     case 16:
-      return DispatchK<16>(e, p, grad, rescale, launch, chunks_override);
+      return DispatchModes<16, 1>(e, p, grad, rescale, launch, chunks_override);
   }
   Fail(SBNB_ERR_INVALID_ARGUMENT, "Unsupported category count.");
+}
+
+// (Re)builds the device copy of the alignment for patterns [begin, end): the
+// range starts at column 0 of the device arrays (TMA bulk copies need 16-byte
+// aligned rows), padded with gap states / zero weights so that the last tile
+// needs no bounds checks (a tile is at most kThreads * 2 patterns).
+void UploadPatternRange(sbnb_engine* e, int64_t begin, int64_t end) {
+  const int64_t count = end - begin;
+  e->tip_pitch = ((count + 511) / 512) * 512 + 512;
+  std::vector<uint8_t> tips(static_cast<size_t>(e->taxon_count) * e->tip_pitch, 4);
+  for (int taxon = 0; taxon < e->taxon_count; taxon++)
+    std::copy(e->host_tips.begin() + static_cast<size_t>(taxon) * e->pattern_count + begin,
+              e->host_tips.begin() + static_cast<size_t>(taxon) * e->pattern_count + end,
+              tips.begin() + static_cast<size_t>(taxon) * e->tip_pitch);
+  std::vector<double> weights(e->tip_pitch, 0.0);
+  std::copy(e->host_weights.begin() + begin, e->host_weights.begin() + end, weights.begin());
+  SBNB_CUDA(cudaStreamSynchronize(e->stream));  // nothing in flight reads the old arrays
+  e->h2d_bytes += e->tips.Upload(tips.data(), tips.size(), e->stream);
+  e->h2d_bytes += e->weights.Upload(weights.data(), weights.size(), e->stream);
+  SBNB_CUDA(cudaStreamSynchronize(e->stream));
+  e->range_begin = begin;
+  e->range_end = end;
 }
 
 void CheckTrees(const sbnb_engine* e, const sbnb_tree_batch* trees, bool rooted) {
@@ -384,12 +418,16 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
     WalkOp* tree_ops = ops + static_cast<size_t>(t) * 2 * (n - 1);
     for (int o = 0; o < n - 1; o++) {
       const PostOp& op = program.post[o];
-      tree_ops[o] = make_int4(op.a, op.b, op.node | (op.flags << 24),
-                              slot_byte(op.dst_slot) | (slot_byte(op.a_slot) << 8) | (slot_byte(op.b_slot) << 16));
+      const int post_flags = op.flags | (op.push_slot >= 0 ? kStackBefore : 0) |
+                             (op.a_src == kFromCur ? kACur : 0) | (op.b_src == kFromCur ? kBCur : 0);
+      tree_ops[o] = make_int4(op.a, op.b, op.node | (post_flags << 24),
+                              slot_byte(op.push_slot) | (slot_byte(op.a_src) << 8) | (slot_byte(op.b_src) << 16));
       const PreOp& pre = program.pre[o];
+      const int pre_flags = pre.flags | (pre.pop_slot >= 0 ? kStackBefore : 0) |
+                            (pre.a_dst == kFromCur ? kACur : 0) | (pre.b_dst == kFromCur ? kBCur : 0);
       tree_ops[n - 1 + o] =
-          make_int4(pre.a, pre.b, pre.node | (pre.flags << 24),
-                    slot_byte(pre.pre_slot) | (slot_byte(pre.a_dst_slot) << 8) | (slot_byte(pre.b_dst_slot) << 16));
+          make_int4(pre.a, pre.b, pre.node | (pre_flags << 24),
+                    slot_byte(pre.pop_slot) | (slot_byte(pre.a_dst) << 8) | (slot_byte(pre.b_dst) << 16));
     }
     slots = std::max({slots, program.post_slots, program.pre_slots});
     program.post.clear();
@@ -437,7 +475,7 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
   e->h2d_bytes += batch->models.Upload(models, model_count, s);
   e->h2d_bytes += batch->d_lengths.Upload(lengths, static_cast<size_t>(T) * N, s);
   batch->matrices.Reserve(static_cast<size_t>(batch->vtree_count) * (N - 1) * e->padded_categories *
-                          kMatrixDoubles);
+                          kEdgeDoublesPerCategory);
   batch->logl.Reserve(batch->vtree_count);
   batch->grad.Reserve(static_cast<size_t>(T) * N);
   batch->rgrad.Reserve(static_cast<size_t>(T) * N);
@@ -463,8 +501,8 @@ WalkParams BaseParams(sbnb_engine* e, sbnb_batch* b) {
   p.tips = e->tips.get();
   p.tip_pitch = e->tip_pitch;
   p.weights = e->weights.get();
-  p.pattern_begin = e->range_begin;
-  p.pattern_end = e->range_end;
+  p.pattern_begin = 0;  // the device arrays start at the engine's pattern range
+  p.pattern_end = e->range_end - e->range_begin;
   p.taxon_count = e->taxon_count;
   p.ops = b->ops.get();
   p.vtree_program = b->vtree_program.get();
@@ -525,11 +563,7 @@ void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
       b->rgrad_partial.Reserve(grad_rows);
       SBNB_CUDA(cudaMemsetAsync(b->rgrad_partial.get(), 0, grad_rows * sizeof(double), s));
     }
-    plan = Dispatch(e, p, grad, rescaling, false, chunks);
-    e->scratch.Reserve(static_cast<size_t>(plan.grid) * (b->taxon_count - 1) *
-                       e->patterns_per_thread * 2 * kThreads);
   }
-  p.scratch = e->scratch.get();
   p.logl_partial = b->logl_partial.get();
   p.grad_partial = b->grad_partial.get();
   p.rgrad_partial = b->rgrad_partial.get();
@@ -739,28 +773,18 @@ int sbnb_engine_create(const char* substitution, const char* site, const char* c
     engine->range_end = pattern_count;
     engine->categories = engine->spec.category_count;
     engine->padded_categories = PadCategories(engine->categories);
-    engine->patterns_per_thread = EnvInt("SBNB_PATTERNS_PER_THREAD", 2);
-    if (engine->patterns_per_thread != 1 && engine->patterns_per_thread != 4)
-      engine->patterns_per_thread = 2;
+    Require(engine->padded_categories > 0, "At most 16 rate categories are supported.");
+    engine->patterns_per_thread = EnvInt("SBNB_PATTERNS_PER_THREAD", 2) == 1 ? 1 : 2;
     SBNB_CUDA(cudaStreamCreateWithFlags(&engine->stream, cudaStreamNonBlocking));
     for (int i = 0; i < sbnb_engine::kWalkRing; i++) {
       SBNB_CUDA(cudaEventCreate(&engine->walk_begin[i]));
       SBNB_CUDA(cudaEventCreate(&engine->walk_end[i]));
     }
-    // Tips padded with gap states (and weights with zeros) so the last tile
-    // needs no bounds checks: a tile is at most 128 * 4 patterns.
-    engine->tip_pitch = ((pattern_count + 511) / 512) * 512 + 512;
-    std::vector<uint8_t> tips(static_cast<size_t>(taxon_count) * engine->tip_pitch, 4);
-    for (int taxon = 0; taxon < taxon_count; taxon++)
-      for (int64_t k = 0; k < pattern_count; k++) {
-        const uint8_t s = tip_states[static_cast<size_t>(taxon) * pattern_count + k];
-        tips[static_cast<size_t>(taxon) * engine->tip_pitch + k] = s < 4 ? s : 4;
-      }
-    std::vector<double> weights(engine->tip_pitch, 0.0);
-    std::copy(pattern_weights, pattern_weights + pattern_count, weights.begin());
-    engine->tips.Upload(tips.data(), tips.size(), engine->stream);
-    engine->weights.Upload(weights.data(), weights.size(), engine->stream);
-    SBNB_CUDA(cudaStreamSynchronize(engine->stream));
+    engine->host_tips.resize(static_cast<size_t>(taxon_count) * pattern_count);
+    for (size_t i = 0; i < engine->host_tips.size(); i++)
+      engine->host_tips[i] = tip_states[i] < 4 ? tip_states[i] : 4;
+    engine->host_weights.assign(pattern_weights, pattern_weights + pattern_count);
+    UploadPatternRange(engine.get(), 0, pattern_count);
     *out = engine.release();
   });
 }
@@ -914,8 +938,8 @@ int sbnb_engine_set_pattern_range(sbnb_engine* engine, int64_t begin, int64_t en
     Require(engine != nullptr, "NULL engine.");
     Require(0 <= begin && begin < end && end <= engine->pattern_count,
             "Pattern range must satisfy 0 <= begin < end <= pattern_count.");
-    engine->range_begin = begin;
-    engine->range_end = end;
+    SBNB_CUDA(cudaSetDevice(engine->device));
+    UploadPatternRange(engine, begin, end);
   });
 }
 

@@ -7,31 +7,6 @@
 
 namespace sbnb {
 
-namespace {
-
-// LIFO pool of stack slots; the high-water mark is the stack depth.
-class SlotPool {
- public:
-  int Acquire() {
-    if (!free_.empty()) {
-      const int slot = free_.back();
-      free_.pop_back();
-      return slot;
-    }
-    return high_water_++;
-  }
-  void Release(int slot) {
-    if (slot >= 0) free_.push_back(slot);
-  }
-  int HighWater() const { return high_water_; }
-
- private:
-  std::vector<int> free_;
-  int high_water_ = 0;
-};
-
-}  // namespace
-
 TreeProgram BuildTreeProgram(const int32_t* parent_ids, int node_count_in, int taxon_count) {
   const int n = taxon_count;
   Require(n >= 2, "A tree needs at least 2 taxa.");
@@ -91,31 +66,46 @@ TreeProgram BuildTreeProgram(const int32_t* parent_ids, int node_count_in, int t
   auto is_leaf = [n](int id) { return id < n; };
 
   // ---- post-order program -------------------------------------------------
-  // need[v] = stack slots required to evaluate v's subtree, its own result
-  // included; the child needing more goes first, and the destination reuses a
-  // child's slot, so need = max(first, [first internal] + second, 1).
+  // need[v] = stack depth used while evaluating v's subtree (cur excluded).
+  // With two internal children the first result waits on the stack while the
+  // second subtree is evaluated, so the child needing more goes first:
+  // need = max(first, 1 + second).
   std::vector<int> need(N, 0);
   for (int id = n; id < N; id++) {
-    const int x = std::max(need[program.child0[id]], need[program.child1[id]]);
-    const int y = std::min(need[program.child0[id]], need[program.child1[id]]);
-    need[id] = std::max({x, (x > 0 ? 1 : 0) + y, 1});
+    const int c0 = program.child0[id], c1 = program.child1[id];
+    if (!is_leaf(c0) && !is_leaf(c1)) {
+      const int hi = std::max(need[c0], need[c1]), lo = std::min(need[c0], need[c1]);
+      need[id] = std::max(hi, 1 + lo);
+    } else {
+      need[id] = std::max(need[c0], need[c1]);
+    }
   }
   {
-    SlotPool pool;
-    std::vector<int> slot_of(N, -1);
+    int depth = 0, high_water = 0;
+    int pending_push = -1;  // slot the next emitted op must push cur to
+    std::vector<int> source(N, kFromLeaf);
     // Explicit DFS stack: (node, stage) where stage counts visited children.
     std::vector<std::pair<int, int>> stack;
     stack.push_back({program.root, 0});
     while (!stack.empty()) {
       auto [id, stage] = stack.back();
       const int c0 = program.child0[id], c1 = program.child1[id];
-      const bool c0_first = need[c0] >= need[c1];
+      const bool both = !is_leaf(c0) && !is_leaf(c1);
+      const bool c0_first = is_leaf(c1) || (!is_leaf(c0) && need[c0] >= need[c1]);
       const int first = c0_first ? c0 : c1, second = c0_first ? c1 : c0;
       if (stage == 0) {
         stack.back().second = 1;
         if (!is_leaf(first)) stack.push_back({first, 0});
       } else if (stage == 1) {
         stack.back().second = 2;
+        if (both) {
+          // first's result is in cur; the first op of second's subtree (a
+          // cherry, which does not read cur) pushes it.
+          pending_push = depth;
+          source[first] = depth;
+          depth++;
+          high_water = std::max(high_water, depth);
+        }
         if (!is_leaf(second)) stack.push_back({second, 0});
       } else {
         stack.pop_back();
@@ -123,86 +113,77 @@ TreeProgram BuildTreeProgram(const int32_t* parent_ids, int node_count_in, int t
         op.node = id;
         op.a = c0;
         op.b = c1;
-        op.a_slot = slot_of[c0];
-        op.b_slot = slot_of[c1];
+        op.push_slot = pending_push;
+        pending_push = -1;
+        op.a_src = is_leaf(c0) ? kFromLeaf : source[c0];
+        op.b_src = is_leaf(c1) ? kFromLeaf : source[c1];
+        if (both) depth--;
         op.flags = (is_leaf(c0) ? kALeaf : 0) | (is_leaf(c1) ? kBLeaf : 0) |
                    (id == program.root ? kRoot : 0);
-        if (op.a_slot >= 0) {
-          op.dst_slot = op.a_slot;
-          pool.Release(op.b_slot);
-        } else if (op.b_slot >= 0) {
-          op.dst_slot = op.b_slot;
-        } else {
-          op.dst_slot = pool.Acquire();
-        }
-        slot_of[id] = op.dst_slot;
+        source[id] = kFromCur;
         program.post.push_back(op);
       }
     }
-    program.post_slots = pool.HighWater();
+    Require(depth == 0 && pending_push < 0, "internal error: unbalanced post-order walk");
+    program.post_slots = high_water;
   }
 
   // ---- pre-order program --------------------------------------------------
-  // pre_need[v] = slots needed below v given v's own pre-order partial holds
-  // one; a single internal child overwrites the parent's slot, two internal
-  // children cost one extra slot while the first subtree is walked.
+  // pre_need[v] = stack depth used below v.  With two internal children one
+  // pre-order partial stays in cur (its subtree is walked first) and the other
+  // waits on the stack, so the child needing less goes first:
+  // need = max(1 + first, second).
   std::vector<int> pre_need(N, 0);
   for (int id = n; id < N; id++) {
     const int c0 = program.child0[id], c1 = program.child1[id];
-    const bool i0 = !is_leaf(c0), i1 = !is_leaf(c1);
-    if (i0 && i1) {
+    if (!is_leaf(c0) && !is_leaf(c1)) {
       const int lo = std::min(pre_need[c0], pre_need[c1]);
       const int hi = std::max(pre_need[c0], pre_need[c1]);
       pre_need[id] = std::max(1 + lo, hi);
-    } else if (i0 || i1) {
-      pre_need[id] = pre_need[i0 ? c0 : c1];
     } else {
-      pre_need[id] = 1;
+      pre_need[id] = std::max(pre_need[c0], pre_need[c1]);
     }
   }
   {
-    SlotPool pool;
-    std::vector<int> slot_of(N, -1);
-    std::vector<int> stack;
-    stack.push_back(program.root);
+    int high_water = 0;
+    // (node, slot its pre-order partial is popped from or -1, stack depth on entry)
+    struct Visit {
+      int node, pop_slot, depth;
+    };
+    std::vector<Visit> stack;
+    stack.push_back({program.root, -1, 0});
     while (!stack.empty()) {
-      const int id = stack.back();
+      const Visit visit = stack.back();
       stack.pop_back();
+      const int id = visit.node;
       const int c0 = program.child0[id], c1 = program.child1[id];
       const bool i0 = !is_leaf(c0), i1 = !is_leaf(c1);
       PreOp op{};
       op.node = id;
       op.a = c0;
       op.b = c1;
-      op.pre_slot = slot_of[id];
-      op.a_dst_slot = -1;
-      op.b_dst_slot = -1;
+      op.pop_slot = visit.pop_slot;
+      op.a_dst = kFromLeaf;
+      op.b_dst = kFromLeaf;
       op.flags = (i0 ? 0 : kALeaf) | (i1 ? 0 : kBLeaf) | (id == program.root ? kRoot : 0);
-      // The node's own slot is dead once both children are computed; the
-      // first-walked internal child inherits it.
-      int inherited = op.pre_slot;
       if (i0 && i1) {
         const bool c0_first = pre_need[c0] <= pre_need[c1];
         const int first = c0_first ? c0 : c1, second = c0_first ? c1 : c0;
-        slot_of[first] = inherited >= 0 ? inherited : pool.Acquire();
-        slot_of[second] = pool.Acquire();
+        const int slot = visit.depth;
+        high_water = std::max(high_water, slot + 1);
+        (c0_first ? op.a_dst : op.b_dst) = kFromCur;
+        (c0_first ? op.b_dst : op.a_dst) = slot;
         // LIFO: push the second so the first subtree is walked first.
-        stack.push_back(second);
-        stack.push_back(first);
+        stack.push_back({second, slot, visit.depth});
+        stack.push_back({first, -1, visit.depth + 1});
       } else if (i0 || i1) {
-        const int only = i0 ? c0 : c1;
-        slot_of[only] = inherited >= 0 ? inherited : pool.Acquire();
-        stack.push_back(only);
-      } else {
-        pool.Release(inherited);
+        (i0 ? op.a_dst : op.b_dst) = kFromCur;
+        stack.push_back({i0 ? c0 : c1, -1, visit.depth});
       }
-      if (i0) op.a_dst_slot = slot_of[c0];
-      if (i1) op.b_dst_slot = slot_of[c1];
       program.pre.push_back(op);
     }
-    program.pre_slots = std::max(pool.HighWater(), 1);
+    program.pre_slots = high_water;
   }
-  if (program.post_slots < 1) program.post_slots = 1;
   return program;
 }
 

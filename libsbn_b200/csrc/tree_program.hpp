@@ -9,7 +9,7 @@
 // internal node producing both children's pre-order partials -- but the ORDER
 // is chosen so that a depth-first walk needs only O(log n) live partials
 // (Strahler ordering), which is what lets a pattern tile keep its working set
-// in shared memory instead of round-tripping every partial through HBM.
+// on chip instead of round-tripping every partial through HBM.
 #ifndef SBNB_TREE_PROGRAM_HPP_
 #define SBNB_TREE_PROGRAM_HPP_
 
@@ -18,32 +18,41 @@
 
 namespace sbnb {
 
-// One post-order op: dest = (P_a L_a) o (P_b L_b) for internal node `node`
-// with children a, b (reference child order: sorted by max leaf id).
-// 32 bytes, read by the kernel as two int4.
+// The walk keeps ONE partial -- the result of the previous op -- in registers
+// ("cur") and everything else that is live on a stack.  A depth-first walk
+// consumes most partials immediately (a node's op directly follows the op of its
+// last-visited internal child), so only nodes with two internal children touch
+// the stack: one push and one pop each.
+
+// Operand / destination codes of the op records below.
+enum : int32_t { kFromLeaf = -1, kFromCur = -2 };
+
+// One post-order op: cur = (P_a L_a) o (P_b L_b) for internal node `node` with
+// children a, b (reference child order: sorted by max leaf id).
+// 32 bytes; the debug API copies these records out as 8 x int32.
 struct PostOp {
-  int32_t node;      // destination node id (n..2n-2); its internal index is node-n
-  int32_t a;         // child 0 node id (= its matrix index; a taxon id when a leaf)
-  int32_t b;         // child 1 node id
-  int32_t dst_slot;  // stack slot the result is written to
-  int32_t a_slot;    // stack slot holding child 0's partial (-1 when a leaf)
-  int32_t b_slot;    // stack slot holding child 1's partial (-1 when a leaf)
-  int32_t flags;     // kALeaf | kBLeaf | kRoot
+  int32_t node;       // destination node id (n..2n-2); its internal index is node-n
+  int32_t a;          // child 0 node id (= its matrix index; a taxon id when a leaf)
+  int32_t b;          // child 1 node id
+  int32_t push_slot;  // >= 0: push cur to this stack slot BEFORE executing (else -1)
+  int32_t a_src;      // kFromLeaf, kFromCur or the stack slot to pop child 0's partial from
+  int32_t b_src;      // same for child 1
+  int32_t flags;      // kALeaf | kBLeaf | kRoot
   int32_t pad;
 };
 
-// One pre-order visit of internal node `node` with pre-order partial in
-// `pre_slot` (root: the stationary distribution, no slot): computes the
-// children's pre-order partials, their edge derivatives, and pushes the
-// pre-order partials of internal children.
+// One pre-order visit of internal node `node`, whose pre-order partial is in
+// cur (root: the stationary distribution) or is popped from `pop_slot` first:
+// computes both children's edge derivatives and the pre-order partials of the
+// internal children; one of them stays in cur, the other is pushed.
 struct PreOp {
   int32_t node;
   int32_t a;
   int32_t b;
-  int32_t pre_slot;    // slot of this node's pre-order partial (-1 at the root)
-  int32_t a_dst_slot;  // where child 0's pre-order partial goes (-1 when a leaf)
-  int32_t b_dst_slot;
-  int32_t flags;       // kALeaf | kBLeaf | kRoot
+  int32_t pop_slot;  // >= 0: pop this node's pre-order partial from the slot first (else -1)
+  int32_t a_dst;     // kFromLeaf (nothing to do), kFromCur (stays in cur) or the slot pushed to
+  int32_t b_dst;
+  int32_t flags;     // kALeaf | kBLeaf | kRoot
   int32_t pad;
 };
 
@@ -57,7 +66,7 @@ struct TreeProgram {
   std::vector<int32_t> child0, child1;  // per node id, -1 for leaves
   std::vector<PostOp> post;             // n-1 ops
   std::vector<PreOp> pre;               // n-1 ops
-  int post_slots = 0;                   // stack depth the post-order walk needs
+  int post_slots = 0;                   // stack depth the post-order walk needs (may be 0)
   int pre_slots = 0;
 };
 

@@ -57,7 +57,7 @@ def stack(gradients, key):
     return np.array([g.gradient[key] for g in gradients])
 
 
-@pytest.fixture(params=[1, 2, 4], ids=lambda k: f"K{k}")
+@pytest.fixture(params=[1, 2], ids=lambda k: f"K{k}")
 def patterns_per_thread(request, monkeypatch):
     monkeypatch.setenv("SBNB_PATTERNS_PER_THREAD", str(request.param))
     return request.param

@@ -145,7 +145,7 @@ def tree_program(parent_ids, taxon_count):
 
 def interpret(parent_ids, lengths, patterns, weights, tables):
     """Executes the kernel's op lists with NumPy (all patterns at once): the
-    same slot stack, the same formulas as TreeWalkKernel, no rescaling."""
+    same cur/stack discipline, the same formulas as TreeWalkKernel, no rescaling."""
     n, P = patterns.shape
     C = len(tables["rates"])
     post, pre, slots = tree_program(parent_ids, n)
@@ -162,60 +162,84 @@ def interpret(parent_ids, lengths, patterns, weights, tables):
     def tip(taxon):  # [C][P][4]
         return np.broadcast_to(one_hot[np.minimum(patterns[taxon], 4)], (C, P, 4))
 
+    # ---- post-order: one partial ("cur") in registers, the rest on a stack
     stack = [None] * int(max(slots))
     live = set()
-    stored = {}
+    cur = None  # (node, partial)
+    evolved = {}  # what the kernel streams to its scratch arena: P_x L_x of internal x
     log_likelihood = None
     seen = set()
-    for node, a, b, dst, a_slot, b_slot, flags, _ in post:
-        def child(idx, slot, leaf):
+    for node, a, b, push_slot, a_src, b_src, flags, _ in post:
+        if push_slot >= 0:
+            assert (flags & 3) == 3, "only a cherry may push: it must not read cur"
+            assert cur is not None and push_slot not in live
+            stack[push_slot] = cur
+            live.add(push_slot)
+            cur = None
+
+        def child(idx, src, leaf):
+            nonlocal cur
             if leaf:
-                assert slot == -1
+                assert src == -1
                 return tip(idx)
-            assert slot in live and stack[slot][0] == idx, "child partial not live in its slot"
-            return stack[slot][1]
-        la, lb = child(a, a_slot, flags & 1), child(b, b_slot, flags & 2)
-        assert a in seen or a < n
-        assert b in seen or b < n
-        out = np.einsum("cij,ckj->cki", mats[a], la) * np.einsum("cij,ckj->cki", mats[b], lb)
-        for s in (a_slot, b_slot):
-            live.discard(s)
+            if src == -2:
+                assert cur is not None and cur[0] == idx, "child partial is not the previous result"
+                out = cur[1]
+                cur = None
+                return out
+            assert src in live and stack[src][0] == idx, "child partial not live in its slot"
+            live.discard(src)
+            return stack[src][1]
+        la, lb = child(a, a_src, flags & 1), child(b, b_src, flags & 2)
+        assert cur is None, "cur must have been consumed or pushed"
+        ya = np.einsum("cij,ckj->cki", mats[a], la)
+        yb = np.einsum("cij,ckj->cki", mats[b], lb)
+        if not flags & 1:
+            evolved[a] = ya
+        if not flags & 2:
+            evolved[b] = yb
+        out = ya * yb
         seen.add(node)
+        cur = (node, out)
         if flags & 4:
             site = np.einsum("c,cki,i->k", tables["weights"], out, tables["freqs"])
             log_likelihood = float(weights @ np.log(site))
-        else:
-            assert dst not in live, "destination slot still holds a live partial"
-            stack[dst] = (node, out)
-            live.add(dst)
-            stored[node] = out
-    assert len(seen) == n - 1 and log_likelihood is not None and not live
+    assert len(seen) == n - 1 and log_likelihood is not None and not live and cur[0] == 2 * n - 2
 
+    # ---- pre-order, fused with the edge derivatives
     gradient = np.zeros(N)
-    pre_stack = [None] * int(max(slots))
     live = set()
-    for node, a, b, pre_slot, a_dst, b_dst, flags, _ in pre:
+    cur = None
+    for node, a, b, pop_slot, a_dst, b_dst, flags, _ in pre:
         if flags & 4:
             pp = np.broadcast_to(tables["freqs"], (C, P, 4))
+        elif pop_slot >= 0:
+            assert cur is None and pop_slot in live and stack[pop_slot][0] == node
+            pp = stack[pop_slot][1]
+            live.discard(pop_slot)
         else:
-            assert pre_slot in live and pre_stack[pre_slot][0] == node
-            pp = pre_stack[pre_slot][1]
-            live.discard(pre_slot)
-        la = tip(a) if flags & 1 else stored[a]
-        lb = tip(b) if flags & 2 else stored[b]
-        ya = np.einsum("cij,ckj->cki", mats[a], la)
-        yb = np.einsum("cij,ckj->cki", mats[b], lb)
-        pre_a = np.einsum("cij,cki->ckj", mats[a], pp * yb)
-        pre_b = np.einsum("cij,cki->ckj", mats[b], pp * ya)
-        for child, pre_c, lc, dst, leaf in ((a, pre_a, la, a_dst, flags & 1), (b, pre_b, lb, b_dst, flags & 2)):
-            num = np.einsum("c,cki,ij,ckj->k", tables["weights"] * tables["rates"], pre_c, tables["q"], lc)
-            den = np.einsum("c,cki,cki->k", tables["weights"], pre_c, lc)
-            gradient[child] = weights @ (num / den)
-            if not leaf:
-                assert dst not in live
-                pre_stack[dst] = (child, pre_c)
+            assert cur is not None and cur[0] == node, "pre-order partial is not the forwarded one"
+            pp = cur[1]
+        cur = None
+        ya = np.einsum("cij,ckj->cki", mats[a], tip(a)) if flags & 1 else evolved[a]
+        yb = np.einsum("cij,ckj->cki", mats[b], tip(b)) if flags & 2 else evolved[b]
+        ta, tb = pp * yb, pp * ya
+        den = np.einsum("c,cki,cki->k", tables["weights"], ta, ya)
+        for child_id, t, y, dst, leaf in ((a, ta, ya, a_dst, flags & 1), (b, tb, yb, b_dst, flags & 2)):
+            num = np.einsum("c,cki,ij,ckj->k", tables["weights"] * tables["rates"], t, tables["q"], y)
+            gradient[child_id] = weights @ (num / den)
+            if leaf:
+                assert dst == -1
+                continue
+            pre_c = np.einsum("cij,cki->ckj", mats[child_id], t)
+            if dst == -2:
+                assert cur is None, "only one child may stay in cur"
+                cur = (child_id, pre_c)
+            else:
+                assert dst >= 0 and dst not in live
+                stack[dst] = (child_id, pre_c)
                 live.add(dst)
-    assert not live
+    assert not live and cur is None
     return log_likelihood, gradient, slots
 
 
@@ -245,19 +269,19 @@ def test_programs_reproduce_the_oracle(oracle, taxa, seed):
                 fixed = np.flatnonzero(expect == 0.0)
                 got_grad[fixed] = 0.0
             assert np.max(np.abs(got_grad - expect)) < 1e-9 * np.max(np.abs(expect))
-            assert slots.max() <= int(np.floor(np.log2(taxa))) + 1
+            assert slots.max() <= int(np.floor(np.log2(taxa)))
 
 
 def test_stack_depth_is_logarithmic():
-    """Strahler ordering: ladder trees need a constant number of slots, random
-    trees of 1000 taxa at most floor(log2 n) + 1."""
+    """Strahler ordering: ladder trees need at most one stack slot, random trees
+    of 1000 taxa at most floor(log2 n)."""
     for taxa in (10, 100, 1000):
         _, _, slots = tree_program(trees.ladder_topology(taxa), taxa)
-        assert slots.max() <= 2
+        assert slots.max() <= 1
         rng = np.random.default_rng(taxa)
         for _ in range(5):
             _, _, slots = tree_program(trees.random_unrooted_topology(taxa, rng), taxa)
-            assert 1 <= slots.max() <= int(np.floor(np.log2(taxa))) + 1
+            assert 1 <= slots.max() <= int(np.floor(np.log2(taxa)))
 
 
 def test_malformed_topologies_are_rejected():
