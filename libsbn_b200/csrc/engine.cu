@@ -199,7 +199,7 @@ struct LaunchPlan {
 template <int C, int K, bool GRAD, bool RESCALE>
 LaunchPlan PlanAndLaunch(sbnb_engine* e, WalkParams p, bool launch, int chunks_override) {
   auto kernel = TreeWalkKernel<C, K, GRAD, RESCALE>;
-  const size_t smem = WalkSmemBytes(C, K);
+  const size_t smem = WalkSmemBytes(C, K, GRAD);
   SBNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   int per_sm = 0;

@@ -25,7 +25,7 @@
 //
 // Everything an op needs besides partials -- the transition matrices of both
 // child edges for every category and the tip states of the tile -- is brought
-// into a 4-stage shared-memory ring by TMA bulk copies (cp.async.bulk +
+// into a shared-memory ring by TMA bulk copies (cp.async.bulk +
 // mbarrier), issued two ops ahead by one elected thread; all lanes of a warp
 // read the same matrix element, so matrix loads are shared-memory broadcasts.
 #ifndef SBNB_KERNELS_CUH_
@@ -41,8 +41,10 @@ namespace sbnb {
 
 constexpr int kThreads = 128;  // 4 warps per CTA; warps only meet at the ring's mbarriers
 constexpr int kWarps = kThreads / 32;
-constexpr int kStages = 4;        // ring depth
-constexpr int kPrefetchOps = 2;   // ops in flight ahead of the one being computed
+constexpr int kStages = 8;        // operand ring depth (one stage per op)
+constexpr int kPrefetchOps = 5;   // ops in flight ahead of the one being computed
+constexpr int kScratchStages = 4;   // scratch ring depth (one stage per (pre-order op, category))
+constexpr int kScratchPrefetch = 2; // category steps in flight ahead
 
 // Per (tree, edge) block written by TransitionMatrixKernel, in doubles, C = categories:
 //   [0        .. 16C)  P_c            row-major, c = 0..C-1   (internal child: y = P L)
@@ -88,7 +90,7 @@ struct WalkParams {
   // per-CTA arenas + outputs
   double2* stack;         // [grid][slots][K][C][2][kThreads]
   int32_t* stack_exps;    // [grid][slots][K][kThreads]              (rescaling)
-  double2* scratch;       // [grid][n-1][K][C][2][kThreads]          (gradient mode)
+  double2* scratch;       // [grid][n-1][C][K][2][kThreads]          (gradient mode)
   double* logl_partial;   // [vtree][chunk][warp]
   double* grad_partial;   // [vtree][chunk][warp][2n-1]               (gradient mode)
   double* rgrad_partial;  // same, with d rate_c / d shape as the scalers (C > 1)
@@ -101,8 +103,12 @@ __host__ __device__ constexpr int StageChildDoubles(int C) { return 2 * kTipTabl
 __host__ __device__ constexpr int StageBytes(int C, int K) {
   return 2 * StageChildDoubles(C) * 8 + 2 * kThreads * K;
 }
-__host__ __device__ constexpr size_t WalkSmemBytes(int C, int K) {
-  return static_cast<size_t>(kStages) * StageBytes(C, K) + 2 * kStages * 8 + kModelSmemDoubles * 8;
+// One scratch-ring stage: the evolved partials of both children of a pre-order op
+// for one category, [child][j][half][tid] double2.
+__host__ __device__ constexpr int ScratchStageBytes(int K) { return 2 * K * 2 * kThreads * 16; }
+__host__ __device__ constexpr size_t WalkSmemBytes(int C, int K, bool grad) {
+  return static_cast<size_t>(kStages) * StageBytes(C, K) + 2 * (kStages + kScratchStages) * 8 +
+         kModelSmemDoubles * 8 + (grad ? static_cast<size_t>(kScratchStages) * ScratchStageBytes(K) : 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -163,15 +169,19 @@ __device__ __forceinline__ void MatVecShared(const double* m, const double (&x)[
     y[i] = fma(row[3], x[3], fma(row[2], x[2], fma(row[1], x[1], row[0] * x[0])));
   }
 }
+// x points at K vectors `stride` apart (in units of double[4]).
 template <int K>
-__device__ __forceinline__ void MatVecSharedK(const double* m, const double (&x)[K][4], double (&y)[K][4]) {
+__device__ __forceinline__ void MatVecSharedK(const double* m, const double (*x)[4], double (&y)[K][4],
+                                              int stride) {
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     double row[4];
     Load4(m + 4 * i, row);
 #pragma unroll
-    for (int j = 0; j < K; j++)
-      y[j][i] = fma(row[3], x[j][3], fma(row[2], x[j][2], fma(row[1], x[j][1], row[0] * x[j][0])));
+    for (int j = 0; j < K; j++) {
+      const double* v = x[j * stride];
+      y[j][i] = fma(row[3], v[3], fma(row[2], v[2], fma(row[1], v[1], row[0] * v[0])));
+    }
   }
 }
 // y = M^T x
@@ -285,7 +295,7 @@ __global__ void TransitionMatrixKernel(const ModelTables* __restrict__ models,
 // access is a coalesced 16 B per lane.
 
 template <int C, int K, bool GRAD, bool RESCALE>
-__global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p) {
+__global__ void __launch_bounds__(kThreads, (K == 1 && C <= 4) ? 3 : 2) TreeWalkKernel(const WalkParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -299,21 +309,33 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
   constexpr int kStage = StageBytes(C, K);
   constexpr int kChild = StageChildDoubles(C);
   constexpr int kRow = 2 * kThreads;  // double2 per (j, c) block: [half][tid]
+  // Fetch category c + 1's stack / scratch operands while category c is computed
+  // (only where the registers for it exist).
+  constexpr bool kFetchAhead = (K == 1);
 
   // ---- shared memory carve-up ------------------------------------------------
   unsigned char* const ring = smem_raw;
   uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kStage);
   uint64_t* const empty = full + kStages;
-  double* const q_smem = reinterpret_cast<double*>(empty + kStages);
+  uint64_t* const scratch_full = empty + kStages;
+  uint64_t* const scratch_empty = scratch_full + kScratchStages;
+  double* const q_smem = reinterpret_cast<double*>(scratch_empty + kScratchStages);
   double* const cat_weight_smem = q_smem + 16;
   double* const rate_weight_smem = cat_weight_smem + kMaxCategories;
   double* const drate_weight_smem = rate_weight_smem + kMaxCategories;
   double* const freqs_smem = drate_weight_smem + kMaxCategories;
+  // (16-byte aligned: every region before it is a multiple of 16 bytes)
+  double2* const scratch_ring = reinterpret_cast<double2*>(freqs_smem + 4);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; s++) {
       MbarInit(full + s, 1);
       MbarInit(empty + s, kWarps);
+    }
+#pragma unroll
+    for (int s = 0; s < kScratchStages; s++) {
+      MbarInit(scratch_full + s, 1);
+      MbarInit(scratch_empty + s, kWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -328,6 +350,11 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
   auto block_ptr = [&](double2* base, int index, int j, int c) -> double2* {
     return base + (static_cast<size_t>(index) * K + j) * C * kRow + c * kRow;
   };
+  // scratch arena: [node][c][j][half][tid], so one (node, category) block is contiguous
+  auto scratch_ptr = [&](int index, int j, int c) -> double2* {
+    return my_scratch + ((static_cast<size_t>(index) * C + c) * K + j) * kRow;
+  };
+  uint32_t scratch_sequence = 0;  // (pre-order op, category) steps this CTA has consumed
 
   uint32_t sequence = 0;  // ops this CTA has consumed; stage = sequence % kStages
 
@@ -380,6 +407,27 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
       }
     };
 
+    // Producer (thread 0): one category step of a pre-order op -- the evolved
+    // partials of its internal children, 2 K KB each -- into the scratch ring.
+    auto issue_scratch = [&](uint32_t seq, int local_step) {
+      const int s = seq % kScratchStages;
+      if (seq >= kScratchStages) MbarWait(scratch_empty + s, ((seq / kScratchStages) - 1) & 1);
+      const WalkOp op = __ldg(ops + internal_count + local_step / C);
+      const int c = local_step % C;
+      const int flags = op.z >> 24;
+      constexpr uint32_t kBlockBytes = K * kRow * 16;
+      const uint32_t bytes = ((flags & kALeaf) ? 0 : kBlockBytes) + ((flags & kBLeaf) ? 0 : kBlockBytes);
+      if (bytes == 0) {
+        MbarArrive(scratch_full + s);
+        return;
+      }
+      MbarExpectTx(scratch_full + s, bytes);
+      double2* stage = scratch_ring + static_cast<size_t>(s) * (2 * K * kRow);
+      if (!(flags & kALeaf)) BulkCopy(stage, scratch_ptr(op.x - n, 0, c) - tid, kBlockBytes, scratch_full + s);
+      if (!(flags & kBLeaf))
+        BulkCopy(stage + K * kRow, scratch_ptr(op.y - n, 0, c) - tid, kBlockBytes, scratch_full + s);
+    };
+
     double logl_acc = 0.0;
     const int tile_begin = chunk * p.tiles_per_chunk;
     const int tile_end = min(tile_begin + p.tiles_per_chunk, p.tiles_total);
@@ -400,6 +448,7 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
         ahead = __ldg(ops + min(kPrefetchOps, ops_total - 1));
       }
       __syncwarp();
+      WalkOp op_next = __ldg(ops);
 
       double cur[K][C][4];
       int cur_exp[K];
@@ -418,7 +467,23 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
           ahead = __ldg(ops + min(o + kPrefetchOps + 1, ops_total - 1));
         }
         __syncwarp();
-        const WalkOp op = __ldg(ops + o);
+        const WalkOp op = op_next;
+        op_next = __ldg(ops + min(o + 1, ops_total - 1));
+        if (GRAD && o + 1 >= internal_count && o + 1 < ops_total) {
+          // The next pre-order op reads its internal children's evolved partials
+          // back from the scratch arena: start them on their way from HBM to L2 now.
+          const int next_flags = op_next.z >> 24;
+          constexpr int kBlockLines = K * C * kRow * 16 / 128;
+#pragma unroll
+          for (int child = 0; child < 2; child++) {
+            if (next_flags & (child ? kBLeaf : kALeaf)) continue;
+            const char* block = reinterpret_cast<const char*>(
+                scratch_ptr((child ? op_next.y : op_next.x) - n, 0, 0) - tid);
+#pragma unroll
+            for (int line = 0; line < kBlockLines; line += kThreads)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(block + static_cast<size_t>(line + tid) * 128));
+          }
+        }
         const int stage_index = sequence % kStages;
         MbarWait(full + stage_index, (sequence / kStages) & 1);
         const unsigned char* stage = ring + stage_index * kStage;
@@ -467,33 +532,40 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
 #pragma unroll
             for (int j = 0; j < K; j++) cur_exp[j] = (uses_cur ? cur_exp[j] : 0) + popped_exp[j];
           }
-#pragma unroll
+          // At most one operand comes off the stack (the other one is cur).
+          // The category loop is a real loop -- unrolled it would not fit the
+          // instruction cache -- so cur is rotated through its first slot: each
+          // pass consumes cur[.][0] and appends the new value at the back; after C
+          // passes every category is back in place.
+          const bool a_pop = !a_leaf && !(flags & kACur), b_pop = !b_leaf && !(flags & kBCur);
+          const double2* popped = block_ptr(my_stack, a_pop ? s1 : s2, 0, 0);
+          const double* PA = MA;  // this category's block of child 0 / child 1
+          const double* PB = MB;
+#pragma unroll 1
           for (int c = 0; c < C; c++) {
-            double ya[K][4], yb[K][4];
+            double ya[K][4], yb[K][4], x[K][4];
+            if (a_pop || b_pop) {
+#pragma unroll
+              for (int j = 0; j < K; j++) {
+                const double2 v0 = popped[j * C * kRow], v1 = popped[j * C * kRow + kThreads];
+                x[j][0] = v0.x, x[j][1] = v0.y, x[j][2] = v1.x, x[j][3] = v1.y;
+              }
+              popped += kRow;
+            }
             // ---- child 0
             if (a_leaf) {
 #pragma unroll
-              for (int j = 0; j < K; j++) Load4(MA + c * kTipTableDoubles + tip_a[j] * 4, ya[j]);
+              for (int j = 0; j < K; j++) Load4(PA + tip_a[j] * 4, ya[j]);
             } else {
-              double x[K][4];
               if (flags & kACur) {
-#pragma unroll
-                for (int j = 0; j < K; j++)
-#pragma unroll
-                  for (int i = 0; i < 4; i++) x[j][i] = cur[j][c][i];
+                MatVecSharedK<K>(PA, cur[0], ya, C);
               } else {
-#pragma unroll
-                for (int j = 0; j < K; j++) {
-                  const double2* src = block_ptr(my_stack, s1, j, c);
-                  const double2 v0 = src[0], v1 = src[kThreads];
-                  x[j][0] = v0.x, x[j][1] = v0.y, x[j][2] = v1.x, x[j][3] = v1.y;
-                }
+                MatVecSharedK<K>(PA, x, ya, 1);
               }
-              MatVecSharedK<K>(MA + 16 * c, x, ya);
               if (GRAD) {
 #pragma unroll
                 for (int j = 0; j < K; j++) {
-                  double2* dst = block_ptr(my_scratch, a - n, j, c);
+                  double2* dst = scratch_ptr(a - n, j, c);
                   dst[0] = make_double2(ya[j][0], ya[j][1]);
                   dst[kThreads] = make_double2(ya[j][2], ya[j][3]);
                 }
@@ -502,36 +574,33 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
             // ---- child 1
             if (b_leaf) {
 #pragma unroll
-              for (int j = 0; j < K; j++) Load4(MB + c * kTipTableDoubles + tip_b[j] * 4, yb[j]);
+              for (int j = 0; j < K; j++) Load4(PB + tip_b[j] * 4, yb[j]);
             } else {
-              double x[K][4];
               if (flags & kBCur) {
-#pragma unroll
-                for (int j = 0; j < K; j++)
-#pragma unroll
-                  for (int i = 0; i < 4; i++) x[j][i] = cur[j][c][i];
+                MatVecSharedK<K>(PB, cur[0], yb, C);
               } else {
-#pragma unroll
-                for (int j = 0; j < K; j++) {
-                  const double2* src = block_ptr(my_stack, s2, j, c);
-                  const double2 v0 = src[0], v1 = src[kThreads];
-                  x[j][0] = v0.x, x[j][1] = v0.y, x[j][2] = v1.x, x[j][3] = v1.y;
-                }
+                MatVecSharedK<K>(PB, x, yb, 1);
               }
-              MatVecSharedK<K>(MB + 16 * c, x, yb);
               if (GRAD) {
 #pragma unroll
                 for (int j = 0; j < K; j++) {
-                  double2* dst = block_ptr(my_scratch, b - n, j, c);
+                  double2* dst = scratch_ptr(b - n, j, c);
                   dst[0] = make_double2(yb[j][0], yb[j][1]);
                   dst[kThreads] = make_double2(yb[j][2], yb[j][3]);
                 }
               }
             }
+            PA += a_leaf ? kTipTableDoubles : 16;
+            PB += b_leaf ? kTipTableDoubles : 16;
 #pragma unroll
-            for (int j = 0; j < K; j++)
+            for (int j = 0; j < K; j++) {
 #pragma unroll
-              for (int i = 0; i < 4; i++) cur[j][c][i] = ya[j][i] * yb[j][i];
+              for (int k = 0; k + 1 < C; k++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) cur[j][k][i] = cur[j][k + 1][i];
+#pragma unroll
+              for (int i = 0; i < 4; i++) cur[j][C - 1][i] = ya[j][i] * yb[j][i];
+            }
           }
           if (RESCALE) {
 #pragma unroll
@@ -552,6 +621,17 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
             }
           }
         } else {
+          if (o == internal_count) {
+            // The post-order pass wrote the scratch arena with ordinary stores; the
+            // pre-order pass reads it back through TMA (the async proxy).
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+              for (int step = 0; step < kScratchPrefetch && step < internal_count * C; step++)
+                issue_scratch(scratch_sequence + step, step);
+            }
+            __syncwarp();
+          }
           // ================ pre-order op + edge derivatives ================
           // cur = this node's pre-order partial pp (root: pi).  With y_x = P_x L_x
           // (read back from the scratch arena or looked up for a tip),
@@ -594,49 +674,69 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
           double den[K], num_a[K], num_b[K], rnum_a[K], rnum_b[K];
 #pragma unroll
           for (int j = 0; j < K; j++) den[j] = num_a[j] = num_b[j] = rnum_a[j] = rnum_b[j] = 0.0;
-#pragma unroll
+          // A real loop over the categories, cur rotated through its first slot
+          // (see the post-order op).
+#pragma unroll 1
           for (int c = 0; c < C; c++) {
+            // scratch ring: issue the step kScratchPrefetch ahead, wait for this one
+            {
+              const int local_step = (o - internal_count) * C + c;
+              if (tid == 0 && local_step + kScratchPrefetch < internal_count * C)
+                issue_scratch(scratch_sequence + kScratchPrefetch, local_step + kScratchPrefetch);
+              __syncwarp();
+            }
+            const int scratch_stage = scratch_sequence % kScratchStages;
+            // Waited for even when both children are tips (nothing was copied): a warp
+            // that ran ahead through such steps could otherwise arrive twice in one
+            // phase of scratch_empty.
+            MbarWait(scratch_full + scratch_stage, (scratch_sequence / kScratchStages) & 1);
+            const double2* evolved_a = scratch_ring + static_cast<size_t>(scratch_stage) * (2 * K * kRow) + tid;
+            const double2* evolved_b = evolved_a + K * kRow;
             const double cat_weight = cat_weight_smem[c];
             const double rate_w = rate_weight_smem[c];
             const double drate_w = drate_weight_smem[c];
+            const double* TA = MA + c * kTipTableDoubles;  // tip tables of this category
+            const double* TB = MB + c * kTipTableDoubles;
             double ya[K][4], yb[K][4], da[K][4], db[K][4];
             if (a_leaf) {
 #pragma unroll
               for (int j = 0; j < K; j++) {
-                Load4(MA + c * kTipTableDoubles + tip_a[j] * 4, ya[j]);
-                Load4(MA + (C + c) * kTipTableDoubles + tip_a[j] * 4, da[j]);
+                Load4(TA + tip_a[j] * 4, ya[j]);
+                Load4(TA + C * kTipTableDoubles + tip_a[j] * 4, da[j]);
               }
             } else {
 #pragma unroll
               for (int j = 0; j < K; j++) {
-                const double2* src = block_ptr(my_scratch, a - n, j, c);
-                const double2 v0 = __ldcs(src), v1 = __ldcs(src + kThreads);
+                const double2 v0 = evolved_a[j * kRow], v1 = evolved_a[j * kRow + kThreads];
                 ya[j][0] = v0.x, ya[j][1] = v0.y, ya[j][2] = v1.x, ya[j][3] = v1.y;
               }
-              MatVecSharedK<K>(q_smem, ya, da);
             }
             if (b_leaf) {
 #pragma unroll
               for (int j = 0; j < K; j++) {
-                Load4(MB + c * kTipTableDoubles + tip_b[j] * 4, yb[j]);
-                Load4(MB + (C + c) * kTipTableDoubles + tip_b[j] * 4, db[j]);
+                Load4(TB + tip_b[j] * 4, yb[j]);
+                Load4(TB + C * kTipTableDoubles + tip_b[j] * 4, db[j]);
               }
             } else {
 #pragma unroll
               for (int j = 0; j < K; j++) {
-                const double2* src = block_ptr(my_scratch, b - n, j, c);
-                const double2 v0 = __ldcs(src), v1 = __ldcs(src + kThreads);
+                const double2 v0 = evolved_b[j * kRow], v1 = evolved_b[j * kRow + kThreads];
                 yb[j][0] = v0.x, yb[j][1] = v0.y, yb[j][2] = v1.x, yb[j][3] = v1.y;
               }
-              MatVecSharedK<K>(q_smem, yb, db);
             }
+            // this stage's evolved partials are in registers: hand the stage back
+            __syncwarp();
+            if (lane == 0) MbarArrive(scratch_empty + scratch_stage);
+            scratch_sequence++;
+            if (!a_leaf) MatVecSharedK<K>(q_smem, ya, da, 1);
+            if (!b_leaf) MatVecSharedK<K>(q_smem, yb, db, 1);
             double ta[K][4], tb[K][4];
 #pragma unroll
             for (int j = 0; j < K; j++) {
 #pragma unroll
               for (int i = 0; i < 4; i++) {
-                ta[j][i] = cur[j][c][i] * yb[j][i];
-                tb[j][i] = cur[j][c][i] * ya[j][i];
+                ta[j][i] = cur[j][0][i] * yb[j][i];
+                tb[j][i] = cur[j][0][i] * ya[j][i];
               }
               den[j] = fma(cat_weight, Dot4(ta[j], ya[j]), den[j]);
               const double na = Dot4(ta[j], da[j]), nb = Dot4(tb[j], db[j]);
@@ -648,6 +748,11 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
               }
             }
             // children's pre-order partials: one stays in cur, the other is pushed
+            double keep[K][4];
+#pragma unroll
+            for (int j = 0; j < K; j++)
+#pragma unroll
+              for (int i = 0; i < 4; i++) keep[j][i] = 0.0;
             if (!a_leaf) {
               double pre[K][4];
               MatTVecSharedK<K>(MA + 16 * c, ta, pre);
@@ -655,7 +760,7 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
 #pragma unroll
                 for (int j = 0; j < K; j++)
 #pragma unroll
-                  for (int i = 0; i < 4; i++) cur[j][c][i] = pre[j][i];
+                  for (int i = 0; i < 4; i++) keep[j][i] = pre[j][i];
               } else {
 #pragma unroll
                 for (int j = 0; j < K; j++) {
@@ -672,7 +777,7 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
 #pragma unroll
                 for (int j = 0; j < K; j++)
 #pragma unroll
-                  for (int i = 0; i < 4; i++) cur[j][c][i] = pre[j][i];
+                  for (int i = 0; i < 4; i++) keep[j][i] = pre[j][i];
               } else {
 #pragma unroll
                 for (int j = 0; j < K; j++) {
@@ -681,6 +786,15 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
                   dst[kThreads] = make_double2(pre[j][2], pre[j][3]);
                 }
               }
+            }
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+#pragma unroll
+              for (int k = 0; k + 1 < C; k++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) cur[j][k][i] = cur[j][k + 1][i];
+#pragma unroll
+              for (int i = 0; i < 4; i++) cur[j][C - 1][i] = keep[j][i];
             }
           }
           // ---- per-pattern derivative terms, then one warp reduction per edge
@@ -703,12 +817,14 @@ __global__ void __launch_bounds__(kThreads, 2) TreeWalkKernel(const WalkParams p
             rb = WarpSum(rb);
           }
           if (lane == 0) {
-            // single writer per (row, edge): plain read-modify-write, deterministic
-            grad_row[a] += ga;
-            grad_row[b] += gb;
+            // Single writer per (row, edge), in program order, so the sums are
+            // deterministic; a reduction (no return value) keeps the round trip to
+            // L2 off the warp's critical path.
+            atomicAdd(grad_row + a, ga);
+            atomicAdd(grad_row + b, gb);
             if (C > 1) {
-              rgrad_row[a] += ra;
-              rgrad_row[b] += rb;
+              atomicAdd(rgrad_row + a, ra);
+              atomicAdd(rgrad_row + b, rb);
             }
           }
         }
