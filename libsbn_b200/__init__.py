@@ -6,4 +6,5 @@ not load the CUDA library; the first Engine does, and fails loudly if it has
 not been built.
 """
 from .engine import Engine, PhyloGradient, PhyloModelSpecification, StagedBatch, TreeBatch  # noqa: F401
+from .gp_engine import GPEngine, GPOperations, estimate_branch_lengths  # noqa: F401
 from . import alignment, _capi  # noqa: F401

@@ -1,4 +1,4 @@
-"""ctypes binding of include/sbn_b200.h (the C ABI of libsbn_b200.so).
+"""ctypes binding of include/sbn_b200.h and include/sbn_b200_gp.h (the C ABI of libsbn_b200.so).
 
 Loading is explicit and loud: if the CUDA library has not been built, importing
 this module raises -- there is no Python/NumPy fallback for any compute call.
@@ -84,6 +84,38 @@ SIGNATURES = {
                                            _P(_c.c_int32), _P(_c.c_int32)]),
     "sbnb_debug_model_tables": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p] + [_P(_c.c_double)] * 9),
 }
+
+# Every symbol include/sbn_b200_gp.h declares.
+_QUARTET = [_c.c_void_p, _c.c_int32] + [_P(_c.c_int32), _c.c_int32] * 4
+_GP_GET = (_c.c_int, [_c.c_void_p, _P(_c.c_double)])
+SIGNATURES.update({
+    "sbnb_gp_create": (_c.c_int, [_c.c_int32, _c.c_int64, _P(_c.c_uint8), _P(_c.c_double), _c.c_int64, _c.c_int32,
+                                  _c.c_int32, _c.c_double, _P(_c.c_double), _P(_c.c_double), _c.c_int32,
+                                  _P(_c.c_double), _c.c_int32, _P(_c.c_void_p)]),
+    "sbnb_gp_destroy": (None, [_c.c_void_p]),
+    "sbnb_gp_process_operations": (_c.c_int, [_c.c_void_p, _P(_c.c_int32), _c.c_int64]),
+    "sbnb_gp_set_branch_lengths": _GP_GET,
+    "sbnb_gp_set_branch_lengths_to_constant": (_c.c_int, [_c.c_void_p, _c.c_double]),
+    "sbnb_gp_get_branch_lengths": _GP_GET,
+    "sbnb_gp_reset_log_marginal_likelihood": (_c.c_int, [_c.c_void_p]),
+    "sbnb_gp_get_log_marginal_likelihood": _GP_GET,
+    "sbnb_gp_get_per_gpcsp_log_likelihoods": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_int32, _P(_c.c_double)]),
+    "sbnb_gp_get_per_gpcsp_components_of_full_log_marginal": _GP_GET,
+    "sbnb_gp_get_log_likelihood_matrix": _GP_GET,
+    "sbnb_gp_get_sbn_parameters": _GP_GET,
+    "sbnb_gp_set_sbn_parameters": _GP_GET,
+    "sbnb_gp_get_hybrid_marginals": _GP_GET,
+    "sbnb_gp_set_hybrid_marginals": _GP_GET,
+    "sbnb_gp_log_likelihood_and_derivative": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_int32, _c.c_int32,
+                                                         _P(_c.c_double)]),
+    "sbnb_gp_transition_matrix": (_c.c_int, [_c.c_void_p, _c.c_double, _P(_c.c_double)]),
+    "sbnb_gp_quartet_hybrid_likelihoods": (_c.c_int, _QUARTET + [_P(_c.c_double)]),
+    "sbnb_gp_process_quartet_hybrid_request": (_c.c_int, _QUARTET),
+    "sbnb_gp_get_plv": (_c.c_int, [_c.c_void_p, _c.c_int32, _P(_c.c_double)]),
+    "sbnb_gp_get_rescaling_counts": (_c.c_int, [_c.c_void_p, _P(_c.c_int32)]),
+    "sbnb_gp_launch_count": (_c.c_int64, [_c.c_void_p]),
+    "sbnb_gp_last_kernel_ms": (_c.c_double, [_c.c_void_p]),
+})
 
 MODE_LOG_LIKELIHOOD = 0
 MODE_BRANCH_GRADIENT = 1
