@@ -23,12 +23,14 @@ import libsbn_b200
 
 
 def test_library_exports_every_declared_symbol():
-    header = open(os.path.join(ROOT, "include", "sbn_b200.h")).read()
-    declared = set(re.findall(r"\b(sbnb_[a-z_0-9]+)\s*\(", header))
-    assert len(declared) >= 20
+    declared = set()
+    for name in ("sbn_b200.h", "sbn_b200_gp.h"):
+        header = open(os.path.join(ROOT, "include", name)).read()
+        declared |= set(re.findall(r"\b(sbnb_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 45
     lib = ctypes.CDLL(_capi.LIB_PATH)
     for name in sorted(declared):
-        assert hasattr(lib, name), f"{name} declared in sbn_b200.h but not exported"
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
     assert declared == set(_capi.SIGNATURES), "python binding and header disagree"
 
 
@@ -40,6 +42,30 @@ def test_no_device_means_failure_not_fallback():
         libsbn_b200.Engine(libsbn_b200.PhyloModelSpecification(), np.zeros((3, 5), np.uint8), np.ones(5))
     assert info.value.code == -2  # SBNB_ERR_NO_DEVICE
     assert "no CPU fallback" in str(info.value)
+
+
+def test_gp_engine_without_device_fails_loudly():
+    lib = _capi.load()
+    if lib.sbnb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError) as info:
+        libsbn_b200.GPEngine(np.zeros((3, 5), np.uint8), np.ones(5), 5, 30, 5)
+    assert info.value.code == -2  # SBNB_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(info.value)
+
+
+def test_gp_operation_encoding_matches_the_reference_dump():
+    """GPOperations.* encode the records oracle/gp_dump.cpp flattened from the
+    reference's own GPOperationVector (hello DAG, gp_dag.cpp:255-263)."""
+    from conftest import load_fixture
+    ops = libsbn_b200.GPOperations
+    fx = load_fixture("gp_hello")
+    assert np.array_equal(ops.program([ops.ResetMarginalLikelihood(), ops.IncrementMarginalLikelihood(19, 0, 4)]),
+                          fx["program_marginal_likelihood"])
+    assert np.array_equal(ops.program([ops.UpdateSBNProbabilities(0, 1)]), fx["program_optimize_sbn_parameters"])
+    head = ops.program([ops.ZeroPLV(3), ops.ZeroPLV(8)])
+    assert np.array_equal(head, fx["program_populate_plvs"][:4])
+    assert ops.PrepForMarginalization(9, [8, 7]) == [9, 9, 2, 8, 7]
 
 
 def test_unknown_models_are_rejected_like_the_reference():
