@@ -159,6 +159,12 @@ int sbnb_batch_run(sbnb_engine* engine, sbnb_batch* batch, int32_t mode, int32_t
  * NULL pointers are skipped. */
 int sbnb_batch_fetch(sbnb_engine* engine, sbnb_batch* batch, double* log_likelihoods,
                      double* branch_gradients, double* rate_gradients);
+/* Device addresses of the raw result arrays sbnb_batch_fetch copies out
+ * (fp64: [evaluation_count], [T][2n-1], [T][2n-1]), valid until the batch is
+ * destroyed.  For site-pattern sharding: the ranks sum-all-reduce these in
+ * place (NCCL, on the engine's stream, after sbnb_batch_run) and then fetch. */
+int sbnb_batch_device_results(sbnb_batch* batch, void** log_likelihoods, void** branch_gradients,
+                              void** rate_gradients);
 void sbnb_batch_destroy(sbnb_engine* engine, sbnb_batch* batch);
 int32_t sbnb_batch_evaluation_count(const sbnb_batch* batch);
 
@@ -185,6 +191,30 @@ int sbnb_engine_walk_timing(sbnb_engine* engine, double* total_ms, int64_t* samp
  * same trees, computes partial sums over its range, and the caller
  * sum-all-reduces log-likelihoods and edge derivatives). */
 int sbnb_engine_set_pattern_range(sbnb_engine* engine, int64_t begin, int64_t end);
+
+/* ---- host finishing, split out for site-pattern sharding ------------------ */
+
+/*
+ * The O(n) host tail of FatBeagle::Gradient (fat_beagle.cpp:467-545) applied to
+ * the RAW sums sbnb_batch_fetch returns: fixed-node zeroing of the branch
+ * gradient, central differences of the substitution gradient, the site-model
+ * contraction (fat_beagle.cpp:389-398) and, for rooted trees, the ratio /
+ * root-height and clock gradients (rooted_gradient_transforms.cpp).  All three
+ * inputs are sums over site patterns, so ranks that each hold a pattern range
+ * sum-all-reduce them and call this once; sbnb_gradients_* is exactly
+ * stage + run + fetch + this.  Needs no device.  with_substitution_fd says
+ * whether log_likelihoods carries the [T][2 * coords] finite-difference
+ * evaluations after the T base values (batch staged with SBNB_STAGE_SUBSTITUTION_FD).
+ */
+int sbnb_finish_gradients(const char* substitution, const char* site, const char* clock,
+                          int32_t taxon_count, const sbnb_tree_batch* trees, int32_t rooted,
+                          int32_t with_substitution_fd, const double* log_likelihoods,
+                          const double* branch_gradients, const double* rate_gradients,
+                          const sbnb_gradient_out* out);
+/* Adds the log-determinant Jacobian of the height-ratio transform
+ * (fat_beagle.cpp:82-94) to already reduced rooted log-likelihoods, in place. */
+int sbnb_finish_log_likelihoods_rooted(int32_t taxon_count, const sbnb_tree_batch* trees,
+                                       double* log_likelihoods);
 
 /* ---- host-only diagnostics (no device needed; used by the CPU test-suite) -- */
 

@@ -72,6 +72,11 @@ SIGNATURES = {
     "sbnb_batch_run": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int32, _c.c_int32]),
     "sbnb_batch_fetch": (_c.c_int, [_c.c_void_p, _c.c_void_p, _P(_c.c_double), _P(_c.c_double),
                                     _P(_c.c_double)]),
+    "sbnb_batch_device_results": (_c.c_int, [_c.c_void_p, _P(_c.c_void_p), _P(_c.c_void_p), _P(_c.c_void_p)]),
+    "sbnb_finish_gradients": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int32, _P(TreeBatchStruct),
+                                         _c.c_int32, _c.c_int32, _P(_c.c_double), _P(_c.c_double),
+                                         _P(_c.c_double), _P(GradientOutStruct)]),
+    "sbnb_finish_log_likelihoods_rooted": (_c.c_int, [_c.c_int32, _P(TreeBatchStruct), _P(_c.c_double)]),
     "sbnb_batch_destroy": (None, [_c.c_void_p, _c.c_void_p]),
     "sbnb_batch_evaluation_count": (_c.c_int32, [_c.c_void_p]),
     "sbnb_engine_stream": (_c.c_void_p, [_c.c_void_p]),

@@ -285,6 +285,25 @@ void FiniteDifferenceRows(const ModelSpec& spec, const double* row, double delta
 
 constexpr double kFiniteDifferenceDelta = 1.e-6;  // fat_beagle.cpp:454
 
+// The branch lengths one evaluation of tree t uses, indexed by node id of the
+// bifurcating (2n-1 node) tree.
+void EffectiveBranchLengths(const TreeProgram& program, const sbnb_tree_batch* trees, int t, bool rooted,
+                            int N, double* out) {
+  const double* in = trees->branch_lengths + static_cast<size_t>(t) * trees->node_count;
+  std::copy(in, in + trees->node_count, out);
+  if (program.was_trifurcating) {
+    // Detrifurcate (unrooted_tree.cpp:31-35): the node that takes the old
+    // root's id and the new root both get length 0.
+    out[N - 2] = 0.0;
+    out[N - 1] = 0.0;
+  }
+  if (rooted) {
+    // fat_beagle.cpp:96-101, 507-511
+    const double* rates = trees->rates + static_cast<size_t>(t) * (N - 1);
+    for (int i = 0; i < N - 1; i++) out[i] *= rates[i];
+  }
+}
+
 std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params,
                                   bool rooted, bool with_fd) {
   CheckTrees(e, trees, rooted);
@@ -323,20 +342,7 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
   for (int t = 0; t < T; t++) {
     TreeProgram program = BuildTreeProgram(
         trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1), trees->node_count, n);
-    const double* in = trees->branch_lengths + static_cast<size_t>(t) * trees->node_count;
-    double* out = lengths + static_cast<size_t>(t) * N;
-    std::copy(in, in + trees->node_count, out);
-    if (program.was_trifurcating) {
-      // Detrifurcate (unrooted_tree.cpp:31-35): the node that takes the old
-      // root's id and the new root both get length 0.
-      out[N - 2] = 0.0;
-      out[N - 1] = 0.0;
-    }
-    if (rooted) {
-      // fat_beagle.cpp:96-101, 507-511
-      const double* rates = trees->rates + static_cast<size_t>(t) * (N - 1);
-      for (int i = 0; i < N - 1; i++) out[i] *= rates[i];
-    }
+    EffectiveBranchLengths(program, trees, t, rooted, N, lengths + static_cast<size_t>(t) * N);
     // Pack both programs into the 16-byte records the kernel streams.
     auto slot_byte = [](int32_t slot) { return slot < 0 ? 0xff : (slot & 0xff); };
     Require(program.post_slots < 255 && program.pre_slots < 255 && N < (1 << 24), "Tree too large.");
@@ -589,51 +595,69 @@ void LogLikelihoods(sbnb_engine* e, const sbnb_tree_batch* trees, const double* 
   }
 }
 
-void Gradients(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params, bool rescaling,
-               bool rooted, const sbnb_gradient_out* out) {
+// Host finishing of a gradient evaluation (the O(n) tail of FatBeagle::Gradient,
+// fat_beagle.cpp:467-545) from the raw per-tree sums over site patterns:
+// logl[T (+ T * 2 * fd_coords)], grad[T][N] edge derivatives, rgrad[T][N] the same
+// with d rate_c / d shape as scalers.  Needs no device: every input is a sum over
+// patterns, so under site-pattern sharding the ranks all-reduce the raw sums
+// and each runs this once.
+void FinishGradients(const ModelSpec& spec, int n, const sbnb_tree_batch* trees, bool rooted, int fd_coords,
+                     const double* logl, const double* grad, const double* rgrad,
+                     const sbnb_gradient_out* out) {
   Require(out != nullptr, "NULL gradient output.");
-  const ModelSpec& spec = e->spec;
-  const int fd_coords = spec.SubstitutionGradientSize();
-  auto batch = Stage(e, trees, params, rooted, fd_coords > 0 && out->substitution_model != nullptr);
-  Run(e, batch.get(), SBNB_MODE_BRANCH_GRADIENT, rescaling);
-  const int T = trees->tree_count, n = e->taxon_count, N = 2 * n - 1;
-  std::vector<double> logl(batch->vtree_count), grad(static_cast<size_t>(T) * N),
-      rgrad(static_cast<size_t>(T) * N);
-  Fetch(e, batch.get(), logl.data(), grad.data(), rgrad.data());
+  const int T = trees->tree_count, N = 2 * n - 1;
   if (rooted)
     Require(T == 0 || (trees->node_heights && trees->node_bounds && trees->height_ratios),
             "Rooted gradients need node_heights, node_bounds and height_ratios.");
+  const int categories = spec.category_count;
+  std::vector<double> g(N), lengths(N);
   for (int t = 0; t < T; t++) {
-    const TreeProgram& tree = batch->programs[t];
-    double* g = grad.data() + static_cast<size_t>(t) * N;
-    const double* rg = rgrad.data() + static_cast<size_t>(t) * N;
-    const double* lengths = batch->lengths.data() + static_cast<size_t>(t) * N;
+    const TreeProgram tree = BuildTreeProgram(
+        trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1), trees->node_count, n);
+    std::copy(grad + static_cast<size_t>(t) * N, grad + static_cast<size_t>(t + 1) * N, g.begin());
     if (out->log_likelihood) out->log_likelihood[t] = logl[t];
-    if (out->substitution_model && batch->fd_coords > 0) {
+    if (out->substitution_model && fd_coords > 0) {
       // Central differences; the rooted Jacobian term cancels (fat_beagle.cpp:431).
-      const double* fd = logl.data() + T + static_cast<size_t>(t) * 2 * batch->fd_coords;
-      for (int k = 0; k < batch->fd_coords; k++)
-        out->substitution_model[static_cast<size_t>(t) * batch->fd_coords + k] =
+      const double* fd = logl + T + static_cast<size_t>(t) * 2 * fd_coords;
+      for (int k = 0; k < fd_coords; k++)
+        out->substitution_model[static_cast<size_t>(t) * fd_coords + k] =
             (fd[2 * k] - fd[2 * k + 1]) / (2. * kFiniteDifferenceDelta);
     }
-    if (out->site_model && e->categories > 1)
-      out->site_model[t] = DiscreteSiteModelGradient(N, lengths, rg);  // fat_beagle.cpp:389-398
+    if (out->site_model && categories > 1) {
+      EffectiveBranchLengths(tree, trees, t, rooted, N, lengths.data());
+      out->site_model[t] =
+          DiscreteSiteModelGradient(N, lengths.data(), rgrad + static_cast<size_t>(t) * N);  // fat_beagle.cpp:389-398
+    }
     if (rooted) {
       const RootedView view = ViewOf(trees, t, n);
       if (out->ratios_root_height) {
-        const std::vector<double> ratios = RatioGradientOfBranchGradient(tree, view, g);
+        const std::vector<double> ratios = RatioGradientOfBranchGradient(tree, view, g.data());
         std::copy(ratios.begin(), ratios.end(), out->ratios_root_height + static_cast<size_t>(t) * (n - 1));
       }
       if (out->clock_model) {
-        const std::vector<double> clock = ClockGradient(tree, view, g);
+        const std::vector<double> clock = ClockGradient(tree, view, g.data());
         std::copy(clock.begin(), clock.end(), out->clock_model + static_cast<size_t>(t) * view.rate_count);
       }
     } else if (out->branch_lengths) {
       // "We want the fixed node to have a zero gradient" (fat_beagle.cpp:498-500).
       g[tree.child1[tree.root]] = 0.0;
-      std::copy(g, g + N, out->branch_lengths + static_cast<size_t>(t) * N);
+      std::copy(g.begin(), g.end(), out->branch_lengths + static_cast<size_t>(t) * N);
     }
   }
+}
+
+void Gradients(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params, bool rescaling,
+               bool rooted, const sbnb_gradient_out* out) {
+  Require(out != nullptr, "NULL gradient output.");
+  const int fd_coords = e->spec.SubstitutionGradientSize();
+  auto batch = Stage(e, trees, params, rooted, fd_coords > 0 && out->substitution_model != nullptr);
+  Run(e, batch.get(), SBNB_MODE_BRANCH_GRADIENT, rescaling);
+  const int T = trees->tree_count, N = 2 * e->taxon_count - 1;
+  std::vector<double> logl(batch->vtree_count), grad(static_cast<size_t>(T) * N),
+      rgrad(static_cast<size_t>(T) * N);
+  Fetch(e, batch.get(), logl.data(), grad.data(), rgrad.data());
+  FinishGradients(e->spec, e->taxon_count, trees, rooted, batch->fd_coords, logl.data(), grad.data(),
+                  rgrad.data(), out);
 }
 
 }  // namespace
@@ -764,6 +788,44 @@ int sbnb_gradients_rooted(sbnb_engine* engine, const sbnb_tree_batch* trees, con
   });
 }
 
+int sbnb_finish_gradients(const char* substitution, const char* site, const char* clock,
+                          int32_t taxon_count, const sbnb_tree_batch* trees, int32_t rooted,
+                          int32_t with_substitution_fd, const double* log_likelihoods,
+                          const double* branch_gradients, const double* rate_gradients,
+                          const sbnb_gradient_out* out) {
+  return Guard([&] {
+    Require(substitution && site && clock, "NULL model specification string.");
+    Require(trees != nullptr, "NULL tree batch.");
+    Require(taxon_count >= 3, "Need at least 3 taxa.");
+    const ModelSpec spec = ModelSpec::Parse(substitution, site, clock);
+    Require(trees->tree_count == 0 || (trees->parent_ids && trees->branch_lengths),
+            "NULL parent_ids / branch_lengths.");
+    Require(trees->tree_count == 0 || (log_likelihoods && branch_gradients),
+            "NULL log_likelihoods / branch_gradients.");
+    Require(spec.category_count == 1 || trees->tree_count == 0 || rate_gradients != nullptr,
+            "rate_gradients are required for a multi-category site model.");
+    Require(!rooted || trees->tree_count == 0 || trees->rates != nullptr,
+            "Rooted evaluation needs per-branch rates (RootedTree::rates_).");
+    FinishGradients(spec, taxon_count, trees, rooted != 0,
+                    with_substitution_fd ? spec.SubstitutionGradientSize() : 0, log_likelihoods,
+                    branch_gradients, rate_gradients, out);
+  });
+}
+
+int sbnb_finish_log_likelihoods_rooted(int32_t taxon_count, const sbnb_tree_batch* trees,
+                                       double* log_likelihoods) {
+  return Guard([&] {
+    Require(trees != nullptr, "NULL tree batch.");
+    Require(trees->tree_count == 0 || (log_likelihoods && trees->node_heights && trees->node_bounds),
+            "Rooted log likelihoods need node_heights and node_bounds.");
+    for (int t = 0; t < trees->tree_count; t++) {
+      const TreeProgram tree = BuildTreeProgram(
+          trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1), trees->node_count, taxon_count);
+      log_likelihoods[t] += LogDetJacobianHeightRatios(tree, ViewOf(trees, t, taxon_count));
+    }
+  });
+}
+
 int sbnb_batch_stage(sbnb_engine* engine, const sbnb_tree_batch* trees, const double* params,
                      int32_t stage_flags, sbnb_batch** out) {
   return Guard([&] {
@@ -787,6 +849,16 @@ int sbnb_batch_fetch(sbnb_engine* engine, sbnb_batch* batch, double* log_likelih
   return Guard([&] {
     Require(engine && batch, "NULL argument.");
     Fetch(engine, batch, log_likelihoods, branch_gradients, rate_gradients);
+  });
+}
+
+int sbnb_batch_device_results(sbnb_batch* batch, void** log_likelihoods, void** branch_gradients,
+                              void** rate_gradients) {
+  return Guard([&] {
+    Require(batch != nullptr, "NULL batch.");
+    if (log_likelihoods) *log_likelihoods = batch->logl.get();
+    if (branch_gradients) *branch_gradients = batch->grad.get();
+    if (rate_gradients) *rate_gradients = batch->rgrad.get();
   });
 }
 
