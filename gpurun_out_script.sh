@@ -1,8 +1,2 @@
-mkdir -p gpurun_out
-nvidia-smi -L
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"; tail -3 gpurun_out/bench_n1.err
-cat gpurun_out/bench_n1.json | head -c 4000
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench2 exit $?"; tail -3 gpurun_out/bench_n2.err
-cat gpurun_out/bench_n2.json | head -c 1500
+python tools/e2e_breakdown.py
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3

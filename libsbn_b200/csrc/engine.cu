@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <exception>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -80,13 +83,12 @@ struct sbnb_engine {
   DeviceArray<double2> stack;    // per-CTA partial stacks
   DeviceArray<int32_t> stack_exps;
 
-  ~sbnb_engine() {
-    for (int i = 0; i < kWalkRing; i++) {
-      if (walk_begin[i]) cudaEventDestroy(walk_begin[i]);
-      if (walk_end[i]) cudaEventDestroy(walk_end[i]);
-    }
-    if (stream) cudaStreamDestroy(stream);
-  }
+  // A destroyed batch parks its device arrays here so the next Stage() of a
+  // same-sized collection (the one-call entry points stage per call) neither
+  // cudaMallocs nor cudaFrees (cudaFree synchronises the device).
+  sbnb_batch* spare = nullptr;
+
+  ~sbnb_engine();
 };
 
 struct sbnb_batch {
@@ -114,7 +116,34 @@ struct sbnb_batch {
   int chunks = 1;
 };
 
+sbnb_engine::~sbnb_engine() {
+  delete spare;
+  for (int i = 0; i < kWalkRing; i++) {
+    if (walk_begin[i]) cudaEventDestroy(walk_begin[i]);
+    if (walk_end[i]) cudaEventDestroy(walk_end[i]);
+  }
+  if (stream) cudaStreamDestroy(stream);
+}
+
 namespace {
+
+// Parks a finished batch in its engine for reuse (see sbnb_engine::spare).
+void Recycle(sbnb_engine* e, sbnb_batch* batch) {
+  if (!batch) return;
+  if (e && !e->spare) {
+    batch->programs.clear();
+    batch->lengths.clear();
+    batch->last_mode = -1;
+    e->spare = batch;
+  } else {
+    delete batch;
+  }
+}
+struct BatchRecycler {
+  sbnb_engine* engine;
+  void operator()(sbnb_batch* batch) const { Recycle(engine, batch); }
+};
+using BatchPtr = std::unique_ptr<sbnb_batch, BatchRecycler>;
 
 struct LaunchPlan {
   int tiles_total, tiles_per_chunk, chunks, grid;
@@ -285,6 +314,36 @@ void FiniteDifferenceRows(const ModelSpec& spec, const double* row, double delta
 
 constexpr double kFiniteDifferenceDelta = 1.e-6;  // fat_beagle.cpp:454
 
+// Host-side data parallelism over the trees of a batch (what the reference's
+// TaskProcessor thread pool does, task_processor.hpp:43-112): contiguous chunks,
+// one std::thread each; the first exception is rethrown on the calling thread.
+template <typename F>
+void ParallelOverTrees(int count, F&& body) {
+  const int workers = std::max(1, std::min<int>({static_cast<int>(std::thread::hardware_concurrency()), 16,
+                                                 count / 32}));
+  if (workers <= 1) {
+    for (int t = 0; t < count; t++) body(t);
+    return;
+  }
+  std::vector<std::thread> threads;
+  std::exception_ptr failure;
+  std::mutex failure_mutex;
+  for (int w = 0; w < workers; w++) {
+    threads.emplace_back([&, w] {
+      try {
+        const int begin = static_cast<int>(static_cast<int64_t>(count) * w / workers);
+        const int end = static_cast<int>(static_cast<int64_t>(count) * (w + 1) / workers);
+        for (int t = begin; t < end; t++) body(t);
+      } catch (...) {
+        std::lock_guard<std::mutex> lock(failure_mutex);
+        if (!failure) failure = std::current_exception();
+      }
+    });
+  }
+  for (auto& thread : threads) thread.join();
+  if (failure) std::rethrow_exception(failure);
+}
+
 // The branch lengths one evaluation of tree t uses, indexed by node id of the
 // bifurcating (2n-1 node) tree.
 void EffectiveBranchLengths(const TreeProgram& program, const sbnb_tree_batch* trees, int t, bool rooted,
@@ -304,14 +363,15 @@ void EffectiveBranchLengths(const TreeProgram& program, const sbnb_tree_batch* t
   }
 }
 
-std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params,
-                                  bool rooted, bool with_fd) {
+BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params, bool rooted,
+               bool with_fd) {
   CheckTrees(e, trees, rooted);
   const ModelSpec& spec = e->spec;
   Require(spec.param_count == 0 || params != nullptr || trees->tree_count == 0,
           "NULL phylo model parameter matrix.");
   SBNB_CUDA(cudaSetDevice(e->device));
-  auto batch = std::make_unique<sbnb_batch>();
+  BatchPtr batch(e->spare ? e->spare : new sbnb_batch(), BatchRecycler{e});
+  e->spare = nullptr;
   const int T = trees->tree_count, n = e->taxon_count, N = 2 * n - 1;
   batch->tree_count = T;
   batch->taxon_count = n;
@@ -337,9 +397,9 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
   double* lengths = e->staging.Take<double>(static_cast<size_t>(T) * N);
 
   // Programs + branch lengths.
-  batch->programs.reserve(T);
-  int slots = 1;
-  for (int t = 0; t < T; t++) {
+  batch->programs.resize(T);
+  std::vector<int> tree_slots(T, 1);
+  ParallelOverTrees(T, [&](int t) {
     TreeProgram program = BuildTreeProgram(
         trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1), trees->node_count, n);
     EffectiveBranchLengths(program, trees, t, rooted, N, lengths + static_cast<size_t>(t) * N);
@@ -360,14 +420,14 @@ std::unique_ptr<sbnb_batch> Stage(sbnb_engine* e, const sbnb_tree_batch* trees, 
           make_int4(pre.a, pre.b, pre.node | (pre_flags << 24),
                     slot_byte(pre.pop_slot) | (slot_byte(pre.a_dst) << 8) | (slot_byte(pre.b_dst) << 16));
     }
-    slots = std::max({slots, program.post_slots, program.pre_slots});
+    tree_slots[t] = std::max(program.post_slots, program.pre_slots);
     program.post.clear();
     program.post.shrink_to_fit();
     program.pre.clear();
     program.pre.shrink_to_fit();
-    batch->programs.push_back(std::move(program));
-  }
-  batch->slots = slots;
+    batch->programs[t] = std::move(program);
+  });
+  batch->slots = std::max(1, *std::max_element(tree_slots.begin(), tree_slots.end()));
   batch->lengths.assign(lengths, lengths + static_cast<size_t>(T) * N);
 
   // Models: one table per distinct consecutive parameter row (+ its FD rows).
@@ -603,17 +663,20 @@ void LogLikelihoods(sbnb_engine* e, const sbnb_tree_batch* trees, const double* 
 // and each runs this once.
 void FinishGradients(const ModelSpec& spec, int n, const sbnb_tree_batch* trees, bool rooted, int fd_coords,
                      const double* logl, const double* grad, const double* rgrad,
-                     const sbnb_gradient_out* out) {
+                     const sbnb_gradient_out* out, const std::vector<TreeProgram>* programs = nullptr) {
   Require(out != nullptr, "NULL gradient output.");
   const int T = trees->tree_count, N = 2 * n - 1;
   if (rooted)
     Require(T == 0 || (trees->node_heights && trees->node_bounds && trees->height_ratios),
             "Rooted gradients need node_heights, node_bounds and height_ratios.");
   const int categories = spec.category_count;
-  std::vector<double> g(N), lengths(N);
-  for (int t = 0; t < T; t++) {
-    const TreeProgram tree = BuildTreeProgram(
-        trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1), trees->node_count, n);
+  ParallelOverTrees(T, [&](int t) {
+    std::vector<double> g(N), lengths(N);
+    TreeProgram rebuilt;
+    if (!programs)
+      rebuilt = BuildTreeProgram(trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1),
+                                 trees->node_count, n);
+    const TreeProgram& tree = programs ? (*programs)[t] : rebuilt;
     std::copy(grad + static_cast<size_t>(t) * N, grad + static_cast<size_t>(t + 1) * N, g.begin());
     if (out->log_likelihood) out->log_likelihood[t] = logl[t];
     if (out->substitution_model && fd_coords > 0) {
@@ -643,7 +706,7 @@ void FinishGradients(const ModelSpec& spec, int n, const sbnb_tree_batch* trees,
       g[tree.child1[tree.root]] = 0.0;
       std::copy(g.begin(), g.end(), out->branch_lengths + static_cast<size_t>(t) * N);
     }
-  }
+  });
 }
 
 void Gradients(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params, bool rescaling,
@@ -657,7 +720,7 @@ void Gradients(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
       rgrad(static_cast<size_t>(T) * N);
   Fetch(e, batch.get(), logl.data(), grad.data(), rgrad.data());
   FinishGradients(e->spec, e->taxon_count, trees, rooted, batch->fd_coords, logl.data(), grad.data(),
-                  rgrad.data(), out);
+                  rgrad.data(), out, &batch->programs);
 }
 
 }  // namespace
@@ -864,7 +927,7 @@ int sbnb_batch_device_results(sbnb_batch* batch, void** log_likelihoods, void** 
 
 void sbnb_batch_destroy(sbnb_engine* engine, sbnb_batch* batch) {
   if (engine) cudaSetDevice(engine->device);
-  delete batch;
+  Recycle(engine, batch);
 }
 
 int32_t sbnb_batch_evaluation_count(const sbnb_batch* batch) {
