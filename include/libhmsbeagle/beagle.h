@@ -1,23 +1,26 @@
 /*
- * oracle/libhmsbeagle/beagle.h -- TEST INFRASTRUCTURE, not product code.
+ * libhmsbeagle/beagle.h -- the INNER drop-in boundary of libsbn_b200: the subset
+ * of the BEAGLE C API that phylovi/libsbn links against.
  *
- * Declarations-only stand-in for the public header of the third-party BEAGLE
- * library (beagle-dev/beagle-lib, branch hmc-clock, unpinned: reference
- * README.md:16-19, SConstruct:187-197), which is NOT vendored in
- * /root/reference and cannot be installed offline.  It declares exactly the 17
- * C entry points, 2 structs and the flag/return-code enums that the reference
- * calls (all call sites: src/fat_beagle.cpp; flag names:
+ * BEAGLE (beagle-dev/beagle-lib, branch hmc-clock, unpinned: reference
+ * README.md:16-19, SConstruct:187-197) is a third-party dependency that is NOT
+ * vendored in the reference tree.  This header declares exactly the 17 C entry
+ * points, 2 structs and the flag / return-code enums that the reference calls
+ * (all call sites: src/fat_beagle.cpp; flag names:
  * src/beagle_flag_names.hpp:22-54; python enum: src/pylibsbn.cpp:448-475), so
- * that (1) the UNMODIFIED reference host code compiles against it and (2) both
- * the CPU restatement (oracle/beagle_cpu.cpp) and the GPU-backed compatibility
- * shim (libsbn_b200/csrc/beagle_shim.cu) implement the same ABI.
+ * that the UNMODIFIED reference host code compiles against it.  Two libraries
+ * implement this ABI:
+ *   - libsbn_b200/csrc/beagle_shim.cu -> libhmsbeagle_b200.so: every call runs on
+ *     the B200 (the product's compatibility path: relink, nothing else changes);
+ *   - oracle/beagle_cpu.cpp: the CPU restatement used only as the test oracle.
+ * The performance path is the outer boundary, include/sbn_b200.h.
  *
  * Written from the reference's call sites and the published BEAGLE API
  * description; bit positions follow the name table in
  * src/beagle_flag_names.hpp:22-54.
  */
-#ifndef ORACLE_LIBHMSBEAGLE_BEAGLE_H_
-#define ORACLE_LIBHMSBEAGLE_BEAGLE_H_
+#ifndef SBNB_LIBHMSBEAGLE_BEAGLE_H_
+#define SBNB_LIBHMSBEAGLE_BEAGLE_H_
 
 #ifdef __cplusplus
 extern "C" {
@@ -155,4 +158,4 @@ int beagleCalculateRootLogLikelihoods(int instance, const int* bufferIndices,
 }
 #endif
 
-#endif /* ORACLE_LIBHMSBEAGLE_BEAGLE_H_ */
+#endif /* SBNB_LIBHMSBEAGLE_BEAGLE_H_ */

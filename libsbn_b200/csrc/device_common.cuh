@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cfenv>
 #include <new>
 #include <string>
 
@@ -90,8 +91,21 @@ class PinnedArena {
 };
 
 
+// Every C-ABI entry point runs inside Guard: exceptions become error codes, and
+// the caller's floating-point environment comes back exactly as it went in.  The
+// reference branches on sticky FE_OVERFLOW / FE_UNDERFLOW flags
+// (sbn_probability.cpp:278-281), so a flag raised in here (an exp() that underflows
+// while building a model table, or inside the CUDA driver) would change what its
+// next SBN training computes.
+struct FloatingPointEnvironmentKeeper {
+  std::fenv_t saved;
+  FloatingPointEnvironmentKeeper() { std::fegetenv(&saved); }
+  ~FloatingPointEnvironmentKeeper() { std::fesetenv(&saved); }
+};
+
 template <typename F>
 int Guard(F&& body) {
+  FloatingPointEnvironmentKeeper keep_caller_environment;
   try {
     body();
     return SBNB_OK;

@@ -786,6 +786,7 @@ int sbnb_engine_create(const char* substitution, const char* site, const char* c
 
 void sbnb_engine_destroy(sbnb_engine* engine) {
   if (!engine) return;
+  FloatingPointEnvironmentKeeper keep_caller_environment;
   cudaSetDevice(engine->device);
   delete engine;
 }
@@ -926,6 +927,7 @@ int sbnb_batch_device_results(sbnb_batch* batch, void** log_likelihoods, void** 
 }
 
 void sbnb_batch_destroy(sbnb_engine* engine, sbnb_batch* batch) {
+  FloatingPointEnvironmentKeeper keep_caller_environment;
   if (engine) cudaSetDevice(engine->device);
   Recycle(engine, batch);
 }

@@ -955,6 +955,7 @@ int sbnb_gp_create(int32_t taxon_count, int64_t pattern_count, const uint8_t* ti
 
 void sbnb_gp_destroy(sbnb_gp_engine* engine) {
   if (!engine) return;
+  FloatingPointEnvironmentKeeper keep_caller_environment;
   cudaSetDevice(engine->device);
   delete engine;
 }

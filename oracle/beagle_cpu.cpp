@@ -6,7 +6,7 @@
 //
 // What it is: a plain single-threaded fp64 CPU restatement of the 17 entry
 // points of the third-party BEAGLE library that libsbn calls (all call sites in
-// reference src/fat_beagle.cpp; prototypes in oracle/libhmsbeagle/beagle.h).
+// reference src/fat_beagle.cpp; prototypes in include/libhmsbeagle/beagle.h).
 // BEAGLE itself (beagle-dev/beagle-lib, branch hmc-clock, unpinned) is absent
 // from /root/reference and cannot be installed here, so its published
 // algorithm is restated and parity is anchored on the reference's own call
