@@ -1,6 +1,7 @@
 """The drop-in proof: the UNMODIFIED reference test suites and python module,
 built by integration/Makefile on top of libsbn_b200.so instead of BEAGLE (only
-src/engine.{hpp,cpp} replaced by integration/engine.{hpp,cpp}), run on the device.
+src/engine.{hpp,cpp} and src/gp_engine.{hpp,cpp} replaced by their counterparts in
+integration/), run on the device.
 
 The artefacts are built in the build container (where /root/reference is
 mounted) and travel to the GPU box; the reference's input fixtures were staged
@@ -67,10 +68,17 @@ def test_reference_doctest_suite_passes_on_the_device():
 
 @pytest.mark.gpu
 def test_reference_gp_doctest_suite_passes_on_the_device():
-    """reference src/gp_doctest.cpp: its exact-marginal cross-pins evaluate every
-    topology through Engine (gp_doctest.cpp:110-156), i.e. through the device."""
+    """reference src/gp_doctest.cpp with GPEngine replaced by integration/gp_engine.*
+    (PLVs in HBM, op programs on the device through sbn_b200_gp.h): GP likelihoods,
+    marginals, Brent branch-length optimisation, SBN parameter updates, rescaling
+    and quartet hybrid marginals; its exact-marginal cross-pins also evaluate every
+    topology through Engine (gp_doctest.cpp:110-156)."""
     _compare_with_reference_build(
-        "gp_doctest", ("classical likelihood", "two tree marginal", "marginal likelihood on"), 50)
+        "gp_doctest", ("classical likelihood", "two tree marginal", "marginal likelihood on", "GPEngine",
+                       "gradient calculation", "rescaling", "test populate PLV", "SBN root split",
+                       "GPInstance: simplest hybrid marginal"), 50)
+    with open(_artefact("gp_doctest"), "rb") as handle:
+        assert b"BrentOptimization" not in handle.read(), "the reference GPEngine is still linked in"
 
 
 _PYTHON_CASE = textwrap.dedent("""
