@@ -21,6 +21,7 @@
 #include "common.hpp"
 #include "device_common.cuh"
 #include "kernels.cuh"
+#include "walk_lc.cuh"
 #include "model.hpp"
 #include "rooted.hpp"
 #include "tree_program.hpp"
@@ -31,10 +32,11 @@ namespace {
 
 thread_local std::string g_last_error;
 
-// Category counts the tree walk is instantiated for; other counts run padded
+// Category counts the tree walk is instantiated for (the lanes of a pattern hold
+// one category each, so powers of two); other counts run padded
 // with zero-weight categories.
 int PadCategories(int c) {
-  for (int supported : {1, 2, 3, 4, 8, 16})
+  for (int supported : {1, 2, 4, 8, 16})
     if (c <= supported) return supported;
   return 0;
 }
@@ -62,7 +64,6 @@ struct sbnb_engine {
   int64_t range_begin = 0, range_end = 0;
   int categories = 1;         // C
   int padded_categories = 1;  // instantiated count >= C (extra categories have weight 0)
-  int patterns_per_thread = 2;
   std::vector<uint8_t> host_tips;    // [taxon][pattern], states clamped to 0..4
   std::vector<double> host_weights;  // [pattern]
   cudaStream_t stream = nullptr;
@@ -150,17 +151,18 @@ struct LaunchPlan {
   size_t smem_bytes;
 };
 
+// Plans (and launches) TreeWalkLcKernel, whose tiles are kThreads / C * K patterns.
 template <int C, int K, bool GRAD, bool RESCALE>
-LaunchPlan PlanAndLaunch(sbnb_engine* e, WalkParams p, bool launch, int chunks_override) {
-  auto kernel = TreeWalkKernel<C, K, GRAD, RESCALE>;
-  const size_t smem = WalkSmemBytes(C, K, GRAD);
+LaunchPlan PlanAndLaunchLc(sbnb_engine* e, WalkParams p, bool launch, int chunks_override) {
+  auto kernel = TreeWalkLcKernel<C, K, GRAD, RESCALE>;
+  const size_t smem = LcSmemBytes(C, K, GRAD);
   SBNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   int per_sm = 0;
   SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
-  if (per_sm < 1) Fail(SBNB_ERR_CUDA, "TreeWalkKernel does not fit on an SM.");
+  if (per_sm < 1) Fail(SBNB_ERR_CUDA, "TreeWalkLcKernel does not fit on an SM.");
   const int resident = per_sm * e->sm_count;
-  constexpr int kTilePatterns = kThreads * K;
+  constexpr int kTilePatterns = LcTilePatterns(C, K);
   LaunchPlan plan;
   const int64_t patterns = p.pattern_end - p.pattern_begin;
   plan.tiles_total = static_cast<int>((patterns + kTilePatterns - 1) / kTilePatterns);
@@ -168,8 +170,14 @@ LaunchPlan PlanAndLaunch(sbnb_engine* e, WalkParams p, bool launch, int chunks_o
     plan.chunks = chunks_override;
     plan.tiles_per_chunk = (plan.tiles_total + plan.chunks - 1) / plan.chunks;
   } else {
-    // Enough (tree, chunk) work items to give every resident CTA ~4 of them.
+    // Enough (tree, chunk) work items to give every resident CTA ~4 of them, and
+    // enough chunks per tree that the CTAs resident at any moment work on few
+    // distinct trees: consecutive items are the chunks of one tree, and every tree
+    // in flight keeps its ~0.4 MB of transition matrices in L2 next to the arena
+    // stream (1024 trees at 2 chunks each had 222 trees -- 81 MB -- in flight).
     int64_t want = (4LL * resident + p.vtree_count - 1) / std::max(p.vtree_count, 1);
+    const int in_flight = std::max(1, EnvInt("SBNB_TREES_IN_FLIGHT", 16));
+    want = std::max<int64_t>(want, (resident + in_flight - 1) / in_flight);
     want = std::max<int64_t>(1, std::min<int64_t>(want, plan.tiles_total));
     plan.tiles_per_chunk = static_cast<int>((plan.tiles_total + want - 1) / want);
     plan.chunks = (plan.tiles_total + plan.tiles_per_chunk - 1) / plan.tiles_per_chunk;
@@ -181,8 +189,7 @@ LaunchPlan PlanAndLaunch(sbnb_engine* e, WalkParams p, bool launch, int chunks_o
     p.tiles_total = plan.tiles_total;
     p.tiles_per_chunk = plan.tiles_per_chunk;
     p.chunks = plan.chunks;
-    // Per-CTA arenas: the partial stack and (gradient runs) the scratch arena.
-    const size_t block = static_cast<size_t>(K) * C * 2 * kThreads;  // double2 per partial block
+    const size_t block = static_cast<size_t>(K) * 2 * kThreads;  // double2 per partial block
     const size_t slots = static_cast<size_t>(std::max(p.slots, 1));
     e->stack.Reserve(static_cast<size_t>(plan.grid) * slots * block);
     p.stack = e->stack.get();
@@ -202,38 +209,35 @@ LaunchPlan PlanAndLaunch(sbnb_engine* e, WalkParams p, bool launch, int chunks_o
 }
 
 template <int C, int K>
-LaunchPlan DispatchModes(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
-                         int chunks_override) {
+LaunchPlan DispatchModesLc(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
+                           int chunks_override) {
   if (grad) {
-    return rescale ? PlanAndLaunch<C, K, true, true>(e, p, launch, chunks_override)
-                   : PlanAndLaunch<C, K, true, false>(e, p, launch, chunks_override);
+    return rescale ? PlanAndLaunchLc<C, K, true, true>(e, p, launch, chunks_override)
+                   : PlanAndLaunchLc<C, K, true, false>(e, p, launch, chunks_override);
   }
-  return rescale ? PlanAndLaunch<C, K, false, true>(e, p, launch, chunks_override)
-                 : PlanAndLaunch<C, K, false, false>(e, p, launch, chunks_override);
+  return rescale ? PlanAndLaunchLc<C, K, false, true>(e, p, launch, chunks_override)
+                 : PlanAndLaunchLc<C, K, false, false>(e, p, launch, chunks_override);
 }
 
-template <int C>
-LaunchPlan DispatchK(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
-                     int chunks_override) {
-  if (e->patterns_per_thread == 1) return DispatchModes<C, 1>(e, p, grad, rescale, launch, chunks_override);
-  return DispatchModes<C, 2>(e, p, grad, rescale, launch, chunks_override);
-}
-
+// Patterns per thread: a gradient walk holds ~5 partial-sized arrays per pattern in
+// registers, so 2 (3 resident CTAs); a logL-only walk holds 3, so 4 where the tile
+// (kThreads / C * K patterns) stays a multiple of 16.
 LaunchPlan Dispatch(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
                     int chunks_override) {
   switch (e->padded_categories) {
     case 1:
-      return DispatchK<1>(e, p, grad, rescale, launch, chunks_override);
+      return grad ? DispatchModesLc<1, 2>(e, p, true, rescale, launch, chunks_override)
+                  : DispatchModesLc<1, 4>(e, p, false, rescale, launch, chunks_override);
     case 2:
-      return DispatchK<2>(e, p, grad, rescale, launch, chunks_override);
-    case 3:
-      return DispatchK<3>(e, p, grad, rescale, launch, chunks_override);
+      return grad ? DispatchModesLc<2, 2>(e, p, true, rescale, launch, chunks_override)
+                  : DispatchModesLc<2, 4>(e, p, false, rescale, launch, chunks_override);
     case 4:
-      return DispatchK<4>(e, p, grad, rescale, launch, chunks_override);
-    case 8:  // a thread holds all categories of its patterns in registers: one pattern each
-      return DispatchModes<8, 1>(e, p, grad, rescale, launch, chunks_override);
+      return grad ? DispatchModesLc<4, 2>(e, p, true, rescale, launch, chunks_override)
+                  : DispatchModesLc<4, 4>(e, p, false, rescale, launch, chunks_override);
+    case 8:
+      return DispatchModesLc<8, 2>(e, p, grad, rescale, launch, chunks_override);
     case 16:
-      return DispatchModes<16, 1>(e, p, grad, rescale, launch, chunks_override);
+      return DispatchModesLc<16, 2>(e, p, grad, rescale, launch, chunks_override);
   }
   Fail(SBNB_ERR_INVALID_ARGUMENT, "Unsupported category count.");
 }
@@ -769,7 +773,6 @@ int sbnb_engine_create(const char* substitution, const char* site, const char* c
     engine->categories = engine->spec.category_count;
     engine->padded_categories = PadCategories(engine->categories);
     Require(engine->padded_categories > 0, "At most 16 rate categories are supported.");
-    engine->patterns_per_thread = EnvInt("SBNB_PATTERNS_PER_THREAD", 2) == 1 ? 1 : 2;
     SBNB_CUDA(cudaStreamCreateWithFlags(&engine->stream, cudaStreamNonBlocking));
     for (int i = 0; i < sbnb_engine::kWalkRing; i++) {
       SBNB_CUDA(cudaEventCreate(&engine->walk_begin[i]));

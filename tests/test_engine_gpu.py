@@ -57,15 +57,9 @@ def stack(gradients, key):
     return np.array([g.gradient[key] for g in gradients])
 
 
-@pytest.fixture(params=[1, 2], ids=lambda k: f"K{k}")
-def patterns_per_thread(request, monkeypatch):
-    monkeypatch.setenv("SBNB_PATTERNS_PER_THREAD", str(request.param))
-    return request.param
-
-
 @pytest.mark.parametrize("name", UNROOTED)
 @pytest.mark.parametrize("rescaling", [False, True], ids=["plain", "rescaled"])
-def test_unrooted_log_likelihoods(oracle, name, rescaling, patterns_per_thread):
+def test_unrooted_log_likelihoods(oracle, name, rescaling):
     fx = load_fixture(name)
     engine = engine_of(fx)
     got = engine.log_likelihoods(batch_of(fx), fx["params"], rescaling)
@@ -80,7 +74,7 @@ def test_unrooted_log_likelihoods(oracle, name, rescaling, patterns_per_thread):
 
 @pytest.mark.parametrize("name", UNROOTED)
 @pytest.mark.parametrize("rescaling", [False, True], ids=["plain", "rescaled"])
-def test_unrooted_gradients(oracle, name, rescaling, patterns_per_thread):
+def test_unrooted_gradients(oracle, name, rescaling):
     fx = load_fixture(name)
     engine = engine_of(fx)
     got = engine.gradients(batch_of(fx), fx["params"], rescaling)
@@ -172,13 +166,16 @@ SYNTHETIC = [
     (11, 65, "GTR", "weibull+16", 2, False),
     (50, 300, "HKY", "weibull+4", 3, False),
     (100, 257, "GTR", "weibull+4", 5, False),
+    (9, 700, "GTR", "weibull+5", 3, False),    # 5 and 6 categories pad to 8 lanes
+    (12, 90, "HKY", "weibull+6", 2, True),
+    (30, 5000, "GTR", "weibull+4", 2, False),  # many tiles per (tree, chunk) item
+    (7, 3000, "JC69", "constant", 6, True),
 ]
 
 
 @pytest.mark.parametrize("taxa,patterns,substitution,site,tree_count,rooted", SYNTHETIC)
 @pytest.mark.parametrize("rescaling", [False, True], ids=["plain", "rescaled"])
-def test_synthetic_against_oracle(oracle, taxa, patterns, substitution, site, tree_count, rooted, rescaling,
-                                  patterns_per_thread):
+def test_synthetic_against_oracle(oracle, taxa, patterns, substitution, site, tree_count, rooted, rescaling):
     seed = taxa * 1000 + patterns
     rng = np.random.default_rng(seed)
     states, _ = trees.random_alignment(taxa, patterns, seed, gap_fraction=0.03)
