@@ -284,7 +284,7 @@ def run_ours(args):
     value = total_trees * args.steps / (ms * 1e-3)
     logl_check = staged.fetch()
 
-    # roofline of the dominant kernel (TreeWalkKernel, gradient mode), this rank's launch
+    # roofline of the dominant kernel (TreeWalkLcKernel, gradient mode), this rank's launch
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_source = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -296,7 +296,7 @@ def run_ours(args):
     # What actually binds the fused walk: its real DRAM traffic (ncu, per tree) and
     # its fp64 work (26.1 kflop per pattern x category per tree) against the B200's
     # non-tensor fp64 rate (64 DFMA / clk / SM x 148 SMs x 1.965 GHz = 37.2 TFLOP/s).
-    traffic_per_tree, profile_name = None, "r01_treewalk_v4_ncu_summary.json"
+    traffic_per_tree, profile_name = None, "r01_treewalk_v5_ncu_summary.json"
     profile = os.path.join(ROOT, "profiles", profile_name)
     if os.path.exists(profile):
         traffic_per_tree = json.load(open(profile)).get("dram_bytes_per_tree")
@@ -308,7 +308,7 @@ def run_ours(args):
     binding = max(floors_ms, key=floors_ms.get)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic_per_tree * args.trees if "hbm_real_traffic" in floors_ms else None,
-                "kernel": "TreeWalkKernel<C=4,K=2,GRAD,RESCALE>", "kernel_ms": kernel_ms,
+                "kernel": "TreeWalkLcKernel<C=4,K=2,GRAD,RESCALE>", "kernel_ms": kernel_ms,
                 "kernel_share_of_step": walk_ms / (ms_local if world > 1 else ms),
                 "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_source,
                 "traffic_source": f"profiles/{profile_name} (ncu --set full, dram read+write per tree x trees)",
