@@ -234,6 +234,9 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own output (the version banner it
+        # prints at NCCL_DEBUG=VERSION/WARN, warnings) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

@@ -73,7 +73,7 @@ void sbnb_engine_destroy(sbnb_engine* engine);
 
 /* Engine::GetPhyloModelBlockSpecification (engine.hpp:31): total parameter
  * count K of one row, and (start, length) of a named block such as
- * "GTR rates", "frequencies", "Weibull shape", "clock rate", "entire
+ * "GTR rates", "frequencies", "kappa", "Weibull shape", "Gamma shape", "clock rate", "entire
  * substitution", "entire site", "entire clock".  Unknown key -> error. */
 int32_t sbnb_engine_param_count(const sbnb_engine* engine);
 int sbnb_engine_param_block(const sbnb_engine* engine, const char* key, int32_t* start,

@@ -63,6 +63,24 @@ ModelSpec ModelSpec::Parse(const std::string& substitution, const std::string& s
       Fail(SBNB_ERR_INVALID_ARGUMENT,
            "Site model category count out of range [1,16]: " + site);
     AppendBlock(&spec, "entire site", {{"Weibull shape", 1}});
+  } else if (site.rfind("gamma", 0) == 0) {
+    // Not in the reference (its "Gamma-4" is weibull+4): "gamma" (4 categories) or "gamma+K".
+    spec.site = SiteKind::kGamma;
+    spec.category_count = 4;
+    const auto plus = site.find('+');
+    if (plus != std::string::npos) {
+      try {
+        spec.category_count = std::stoi(site.substr(plus + 1));
+      } catch (const std::exception&) {
+        Fail(SBNB_ERR_INVALID_ARGUMENT, "Site model not known: " + site);
+      }
+    } else if (site != "gamma") {
+      Fail(SBNB_ERR_INVALID_ARGUMENT, "Site model not known: " + site);
+    }
+    if (spec.category_count < 1 || spec.category_count > kMaxCategories)
+      Fail(SBNB_ERR_INVALID_ARGUMENT,
+           "Site model category count out of range [1,16]: " + site);
+    AppendBlock(&spec, "entire site", {{"Gamma shape", 1}});
   } else {
     Fail(SBNB_ERR_INVALID_ARGUMENT, "Site model not known: " + site);
   }
@@ -240,6 +258,74 @@ void BuildSubstitution(const ModelSpec& spec, const double* params, ModelTables*
   }
 }
 
+// P(a, x): power series for x < a + 1, Lentz continued fraction for Q = 1 - P otherwise.
+double RegularizedGammaP(double a, double x) {
+  if (!(x > 0.0)) return 0.0;
+  const double log_prefactor = a * std::log(x) - x - std::lgamma(a);
+  if (x < a + 1.0) {
+    double term = 1.0 / a, sum = term, denominator = a;
+    for (int n = 0; n < 10000; n++) {
+      denominator += 1.0;
+      term *= x / denominator;
+      sum += term;
+      if (std::fabs(term) < std::fabs(sum) * 1e-17) break;
+    }
+    return sum * std::exp(log_prefactor);
+  }
+  const double tiny = 1e-300;
+  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, fraction = d;
+  for (int n = 1; n < 10000; n++) {
+    const double an = -n * (n - a);
+    b += 2.0;
+    d = an * d + b;
+    if (std::fabs(d) < tiny) d = tiny;
+    c = b + an / c;
+    if (std::fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double delta = d * c;
+    fraction *= delta;
+    if (std::fabs(delta - 1.0) < 1e-16) break;
+  }
+  return 1.0 - std::exp(log_prefactor) * fraction;
+}
+
+// Solves P(a, x) = p for x: a small-x / Wilson-Hilferty starting point, then
+// Halley steps on P (pdf and its log-derivative are closed form), kept positive.
+double InverseRegularizedGammaP(double a, double p) {
+  if (!(p > 0.0)) return 0.0;
+  if (!(p < 1.0)) return INFINITY;
+  const double log_gamma = std::lgamma(a);
+  double x;
+  // small-x asymptote P ~ x^a / Gamma(a + 1)
+  const double small = std::exp((std::log(p) + log_gamma + std::log(a)) / a);
+  if (small < 0.3 * (a + 1.0)) {
+    x = small;
+  } else {
+    // Wilson-Hilferty: (x / a)^(1/3) is nearly normal with mean 1 - 1/(9a), variance 1/(9a)
+    const double t = std::sqrt(-2.0 * std::log(p < 0.5 ? p : 1.0 - p));
+    double z = t - (2.30753 + 0.27061 * t) / (1.0 + t * (0.99229 + 0.04481 * t));
+    if (p < 0.5) z = -z;
+    const double cube = 1.0 - 1.0 / (9.0 * a) + z / (3.0 * std::sqrt(a));
+    x = a * cube * cube * cube;
+    if (!(x > 0.0)) x = small;
+  }
+  for (int iteration = 0; iteration < 100; iteration++) {
+    const double error = RegularizedGammaP(a, x) - p;
+    const double pdf = std::exp((a - 1.0) * std::log(x) - x - log_gamma);
+    if (!(pdf > 0.0)) break;
+    const double newton = error / pdf;
+    // Halley correction with d log pdf / dx = (a - 1) / x - 1, limited to a factor 2
+    const double curvature = newton * ((a - 1.0) / x - 1.0);
+    double step = newton / (1.0 - 0.5 * std::min(1.0, std::max(-1.0, curvature)));
+    double next = x - step;
+    if (!(next > 0.0)) next = 0.5 * x;
+    step = x - next;
+    x = next;
+    if (std::fabs(step) <= 1e-16 * x) break;
+  }
+  return x;
+}
+
 void BuildSite(const ModelSpec& spec, const double* params, ModelTables* out) {
   const int count = spec.category_count;
   for (int c = 0; c < kMaxCategories; c++) {
@@ -252,17 +338,38 @@ void BuildSite(const ModelSpec& spec, const double* params, ModelTables* out) {
     return;
   }
   const double shape = params[0];
-  if (!(shape > 0)) Fail(SBNB_ERR_MODEL, "Weibull shape must be positive.");
-  // site_model.cpp:37-62
   double mean_rate = 0, mean_derivative = 0;
   double unscaled_derivative[kMaxCategories];
-  for (int i = 0; i < count; i++) {
-    const double quantile = (2.0 * i + 1.0) / (2.0 * count);
-    out->rates[i] = std::pow(-std::log(1.0 - quantile), 1.0 / shape);
-    mean_rate += out->rates[i];
-    unscaled_derivative[i] =
-        -out->rates[i] * std::log(-std::log(1.0 - quantile)) / (shape * shape);
-    mean_derivative += unscaled_derivative[i];
+  if (spec.site == SiteKind::kGamma) {
+    // Median discretisation of Gamma(shape, rate = shape) (Yang 1994), the same
+    // scheme the reference uses for its Weibull model: category i sits at the
+    // quantile (2i+1)/(2C) and the rates are divided by their mean -- the 1/shape
+    // scale cancels, so the unit-scale quantile g_i = P^-1(shape, q_i) is enough.
+    // d g / d shape by implicit differentiation of P(shape, g) = q:
+    //   dg/da = -(dP/da) / pdf(g),  dP/da by central differences of P (smooth in a).
+    if (!(shape > 0)) Fail(SBNB_ERR_MODEL, "Gamma shape must be positive.");
+    const double h = 1e-5 * std::max(shape, 1.0);
+    for (int i = 0; i < count; i++) {
+      const double quantile = (2.0 * i + 1.0) / (2.0 * count);
+      const double g = InverseRegularizedGammaP(shape, quantile);
+      out->rates[i] = g;
+      mean_rate += g;
+      const double dP_da = (RegularizedGammaP(shape + h, g) - RegularizedGammaP(shape - h, g)) / (2.0 * h);
+      const double log_pdf = (shape - 1.0) * std::log(g) - g - std::lgamma(shape);
+      unscaled_derivative[i] = -dP_da / std::exp(log_pdf);
+      mean_derivative += unscaled_derivative[i];
+    }
+  } else {
+    if (!(shape > 0)) Fail(SBNB_ERR_MODEL, "Weibull shape must be positive.");
+    // site_model.cpp:37-62
+    for (int i = 0; i < count; i++) {
+      const double quantile = (2.0 * i + 1.0) / (2.0 * count);
+      out->rates[i] = std::pow(-std::log(1.0 - quantile), 1.0 / shape);
+      mean_rate += out->rates[i];
+      unscaled_derivative[i] =
+          -out->rates[i] * std::log(-std::log(1.0 - quantile)) / (shape * shape);
+      mean_derivative += unscaled_derivative[i];
+    }
   }
   mean_rate /= count;
   mean_derivative /= count;

@@ -12,7 +12,7 @@
 namespace sbnb {
 
 enum class SubstitutionKind { kJC69, kGTR, kHKY };
-enum class SiteKind { kConstant, kWeibull };
+enum class SiteKind { kConstant, kWeibull, kGamma };
 enum class ClockKind { kNone, kStrict };
 
 // Layout of one row of the phylo_model_params matrix: the reference's
@@ -45,7 +45,7 @@ struct ModelTables {
   double q[16];         // rate matrix Q (unit expected rate)
   double rates[16];     // category rates r_c           (first category_count used)
   double weights[16];   // category proportions p_c
-  double drates[16];    // d r_c / d shape (Weibull; 0 for a constant site model)
+  double drates[16];    // d r_c / d shape (Weibull, Gamma; 0 for a constant site model)
 };
 
 constexpr int kMaxCategories = 16;
@@ -53,7 +53,8 @@ constexpr int kMaxCategories = 16;
 // substitution_model.cpp:17-80 (GTR), substitution_model.hpp:59-74 (JC69).
 // `params` points at the "entire substitution" block of a row.
 void BuildSubstitution(const ModelSpec& spec, const double* params, ModelTables* out);
-// site_model.cpp:37-62 (Weibull median discretisation) / constant.
+// site_model.cpp:37-62 (Weibull median discretisation) / constant / discrete Gamma
+// (an addition: the reference has no Gamma site model; same median discretisation).
 // `params` points at the "entire site" block of a row.
 void BuildSite(const ModelSpec& spec, const double* params, ModelTables* out);
 // Whole row -> tables.
@@ -67,6 +68,11 @@ void StickBreakingInverse(const double* x, int simplex_size, double* y);
 // columns of `vectors`.  P(t) is invariant to eigenvector order and sign, so any
 // accurate solver reproduces Eigen::SelfAdjointEigenSolver's P(t).
 void SymmetricEigen4(const double* matrix, double* values, double* vectors);
+
+// Regularized lower incomplete gamma function P(a, x) and its inverse in x
+// (the quantile function of a unit-scale Gamma distribution with shape a).
+double RegularizedGammaP(double a, double x);
+double InverseRegularizedGammaP(double a, double p);
 
 }  // namespace sbnb
 

@@ -169,7 +169,7 @@ class Engine:
     def param_block_map(self, params):
         """Views into a trees x params matrix by block name (get_phylo_model_param_block_map)."""
         out = {}
-        for key in ("GTR rates", "frequencies", "kappa", "Weibull shape", "clock rate",
+        for key in ("GTR rates", "frequencies", "kappa", "Weibull shape", "Gamma shape", "clock rate",
                     "entire substitution", "entire site", "entire clock", "entire"):
             try:
                 start, length = self.param_block(key)

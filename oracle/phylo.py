@@ -47,8 +47,41 @@ def _c(a, dtype):
     return None if a is None else np.ascontiguousarray(a, dtype=dtype)
 
 
+def gamma_rates(shape, categories):
+    """Discrete Gamma(shape, rate = shape), median discretisation (Yang 1994): the
+    category rates, normalised to mean 1, and d rate / d shape -- from
+    scipy.stats.gamma.ppf, independently of libsbn_b200's own incomplete-gamma code.
+    The derivative is a 4th-order central difference of the normalised rates."""
+    from scipy.stats import gamma as gamma_distribution
+
+    def rates(a):
+        q = (2.0 * np.arange(categories) + 1.0) / (2.0 * categories)
+        g = gamma_distribution.ppf(q, a)
+        return g / g.mean()
+
+    h = 1e-3 * shape
+    derivative = (-rates(shape + 2 * h) + 8 * rates(shape + h) - 8 * rates(shape - h) + rates(shape - 2 * h)) / (12 * h)
+    return rates(shape), derivative
+
+
+def _expand_site(site, params, substitution):
+    """A "gamma+K" site model is handed to the C oracle as explicit category rates
+    ("rates+K": K rates, K derivatives in place of the shape column)."""
+    if not site.startswith("gamma"):
+        return site, params
+    categories = int(site.split("+")[1]) if "+" in site else 4
+    params = np.asarray(params, dtype=np.float64)
+    head = 10 if substitution == "GTR" else 0
+    rows = []
+    for row in params:
+        r, d = gamma_rates(row[head], categories)
+        rows.append(np.concatenate([row[:head], r, d, row[head + 1:]]))
+    return f"rates+{categories}", np.array(rows)
+
+
 def _common(substitution, site, patterns, weights, parent_ids, branch_lengths, params, rescaling,
             use_tip_states, rooted):
+    site, params = _expand_site(site, params, substitution)
     patterns = _c(patterns, np.uint8)
     weights = _c(weights, np.float64)
     parent_ids = _c(parent_ids, np.int32)

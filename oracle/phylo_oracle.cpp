@@ -45,15 +45,21 @@ struct Model {
   bool gtr = false;   // GTR (10 params) vs JC69 (0 params); HKY is expressed as GTR by the caller
   int categories = 1;  // weibull+K (1 param) vs constant
   bool weibull = false;
+  // "rates+K": the row carries K category rates then K d rate / d shape values
+  // (for site models the reference does not have; the caller discretises them).
+  bool explicit_rates = false;
   // state
   double rates6[6] = {1 / 6., 1 / 6., 1 / 6., 1 / 6., 1 / 6., 1 / 6.};
   double freqs[4] = {0.25, 0.25, 0.25, 0.25};
   double evec[16], ivec[16], eval[4], q[16];
   std::vector<double> cat_rates, cat_weights, cat_rate_derivs;
   double shape = 1.0;
+  std::vector<double> given_rates;
 
   int SubstitutionParamCount() const { return gtr ? 10 : 0; }
-  int ParamCount() const { return SubstitutionParamCount() + (weibull ? 1 : 0); }
+  int ParamCount() const {
+    return SubstitutionParamCount() + (weibull ? 1 : 0) + (explicit_rates ? 2 * categories : 0);
+  }
 };
 
 // Largest-off-diagonal Jacobi for a symmetric 4x4.
@@ -152,6 +158,13 @@ void UpdateSite(Model& m) {
   m.cat_rates.assign(C, 1.0);
   m.cat_weights.assign(C, 1.0 / C);
   m.cat_rate_derivs.assign(C, 0.0);
+  if (m.explicit_rates) {
+    if (static_cast<int>(m.given_rates.size()) == 2 * C) {
+      m.cat_rates.assign(m.given_rates.begin(), m.given_rates.begin() + C);
+      m.cat_rate_derivs.assign(m.given_rates.begin() + C, m.given_rates.end());
+    }
+    return;
+  }
   if (!m.weibull) return;
   double mean_rate = 0, mean_derivative = 0;
   std::vector<double> unscaled(C);
@@ -178,6 +191,8 @@ void SetParameters(Model& m, const double* row) {
     std::copy(row + 6, row + 10, m.freqs);
   }
   if (m.weibull) m.shape = row[m.SubstitutionParamCount()];
+  if (m.explicit_rates)
+    m.given_rates.assign(row + m.SubstitutionParamCount(), row + m.SubstitutionParamCount() + 2 * m.categories);
   UpdateSubstitution(m);
   UpdateSite(m);
 }
@@ -535,6 +550,9 @@ Model ParseModel(const char* substitution, const char* site) {
     m.categories = 4;
     const auto plus = st.find('+');
     if (plus != std::string::npos) m.categories = std::stoi(st.substr(plus + 1));
+  } else if (st.rfind("rates+", 0) == 0) {
+    m.explicit_rates = true;
+    m.categories = std::stoi(st.substr(6));
   } else if (st != "constant") {
     Failwith("Site model not known: " + st);
   }

@@ -170,6 +170,10 @@ SYNTHETIC = [
     (12, 90, "HKY", "weibull+6", 2, True),
     (30, 5000, "GTR", "weibull+4", 2, False),  # many tiles per (tree, chunk) item
     (7, 3000, "JC69", "constant", 6, True),
+    # discrete Gamma (not in the reference): the oracle gets scipy's category rates
+    (10, 300, "GTR", "gamma+4", 3, False),
+    (8, 200, "JC69", "gamma+5", 2, True),
+    (12, 150, "HKY", "gamma", 2, False),
 ]
 
 

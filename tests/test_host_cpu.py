@@ -72,7 +72,8 @@ def test_unknown_models_are_rejected_like_the_reference():
     lib = _capi.load()
     out = (ctypes.c_double * 16)()
     for spec, message in [((b"K80", b"constant", b"none"), "Substitution model not known"),
-                          ((b"JC69", b"gamma", b"none"), "Site model not known"),
+                          ((b"JC69", b"invariant", b"none"), "Site model not known"),
+                          ((b"JC69", b"gammaX", b"none"), "Site model not known"),
                           ((b"JC69", b"constant", b"relaxed"), "Clock model not known")]:
         code = lib.sbnb_debug_model_tables(*spec, None, out, None, None, None, None, None, None, None)
         assert code == -1 and message in lib.sbnb_last_error().decode()
@@ -81,7 +82,7 @@ def test_unknown_models_are_rejected_like_the_reference():
 def model_tables(substitution, site, row):
     lib = _capi.load()
     categories = 1
-    if site.startswith("weibull"):
+    if site.startswith(("weibull", "gamma")):
         categories = int(site.split("+")[1]) if "+" in site else 4
     t = {k: np.zeros(s) for k, s in [("evec", 16), ("ivec", 16), ("eval", 4), ("freqs", 4), ("q", 16),
                                      ("rates", categories), ("weights", categories), ("drates", categories)]}
@@ -128,6 +129,28 @@ def test_hky_is_gtr_with_kappa_on_transitions():
     raw = np.array([1, 2, 1, 1, 2, 1.0])
     gtr = model_tables("GTR", "constant", list(raw / raw.sum()) + freqs)
     assert np.allclose(hky["q"], gtr["q"], atol=1e-15)
+
+
+def test_gamma_rates_match_scipy():
+    """Discrete Gamma is an addition (the reference has Weibull only): pinned to
+    scipy.stats.gamma.ppf, median discretisation, rates normalised to mean 1."""
+    from oracle import phylo
+    for shape in (0.05, 0.1, 0.5, 1.0, 2.7, 10.0, 150.0):
+        for categories in (1, 2, 4, 6, 16):
+            t = model_tables("JC69", f"gamma+{categories}", [shape])
+            rates, derivative = phylo.gamma_rates(shape, categories)
+            assert np.allclose(t["rates"], rates, rtol=1e-11, atol=1e-300), (shape, categories)
+            assert np.allclose(t["weights"], 1 / categories)
+            assert abs(t["rates"] @ t["weights"] - 1) < 1e-14
+            # the mean rate is pinned to 1, so the derivatives sum to zero
+            assert abs(t["drates"].sum()) <= 1e-13 * categories * max(1.0, np.abs(t["drates"]).max()), (shape, categories)
+            if shape >= 0.1:  # below, differencing scipy's ppf is the less accurate side
+                scale = np.abs(derivative).max() + 1e-300
+                assert np.abs(t["drates"] - derivative).max() <= 1e-6 * scale, (shape, categories)
+    assert np.allclose(model_tables("GTR", "gamma", [1 / 6] * 6 + [0.25] * 4 + [0.5])["rates"],
+                       phylo.gamma_rates(0.5, 4)[0], rtol=1e-11)
+    with pytest.raises(_capi.SbnbError, match="Gamma shape must be positive"):
+        model_tables("JC69", "gamma+4", [0.0])
 
 
 def test_weibull_rates():
