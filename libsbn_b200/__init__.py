@@ -7,4 +7,5 @@ not been built.
 """
 from .engine import Engine, PhyloGradient, PhyloModelSpecification, StagedBatch, TreeBatch  # noqa: F401
 from .gp_engine import GPEngine, GPOperations, estimate_branch_lengths  # noqa: F401
+from .site_pattern import SitePattern  # noqa: F401
 from . import alignment, _capi  # noqa: F401

@@ -1,4 +1,4 @@
-"""ctypes binding of include/sbn_b200.h and include/sbn_b200_gp.h (the C ABI of libsbn_b200.so).
+"""ctypes binding of include/sbn_b200.h, sbn_b200_gp.h and sbn_b200_patterns.h (the C ABI of libsbn_b200.so).
 
 Loading is explicit and loud: if the CUDA library has not been built, importing
 this module raises -- there is no Python/NumPy fallback for any compute call.
@@ -49,6 +49,8 @@ class GradientOutStruct(ctypes.Structure):
 _P = ctypes.POINTER
 _c = ctypes
 SIGNATURES = {
+    "sbnb_compress_site_patterns": (_c.c_int, [_c.c_int32, _c.c_int64, _c.c_char_p, _c.c_int32, _P(_c.c_uint8),
+                                               _P(_c.c_double), _P(_c.c_int64), _P(_c.c_double)]),
     "sbnb_last_error": (_c.c_char_p, []),
     "sbnb_device_count": (_c.c_int, []),
     "sbnb_engine_create": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int32, _c.c_int64,

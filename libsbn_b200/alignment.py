@@ -1,12 +1,9 @@
-"""Host-side alignment handling: FASTA -> compressed site patterns.
+"""Host-side alignment handling: FASTA parsing and the DNA symbol table.
 
 Mirrors the reference's Alignment::ReadFasta (src/alignment.cpp:41-73) and
-SitePattern (src/site_pattern.cpp:16-131): DNA symbol table with every
-non-ACGT symbol treated as a gap (state 4), identical columns compressed into
-weighted patterns.  Unlike the reference (whose pattern order is the iteration
-order of a std::unordered_map and therefore stdlib-dependent) patterns are
-kept in order of first appearance, which makes runs reproducible; the
-log-likelihood is invariant to the order up to summation rounding.
+SitePattern::GetSymbolTable (src/site_pattern.cpp:16-46): every non-ACGT symbol is a
+gap (state 4).  Compressing identical columns into weighted site patterns
+(SitePattern::Compress) is done on the device: libsbn_b200.site_pattern.SitePattern.
 """
 import numpy as np
 
@@ -61,15 +58,17 @@ def encode(sequences, taxon_names):
     return np.stack(rows)
 
 
-def compress(states):
-    """SitePattern::Compress: uint8 [taxon][site] -> (patterns [taxon][P], weights [P])."""
-    columns = np.ascontiguousarray(states.T)
-    _, first, inverse, counts = np.unique(columns, axis=0, return_index=True, return_inverse=True,
-                                          return_counts=True)
-    order = np.argsort(first, kind="stable")  # first-appearance order
-    patterns = np.ascontiguousarray(columns[first[order]].T)
-    return patterns, counts[order].astype(np.float64)
+def sequences_in_leaf_order(sequences, taxon_names):
+    """Sequences (dict name -> str) as a list in leaf-id order."""
+    for name in taxon_names:
+        if name not in sequences:
+            raise RuntimeError(f"Taxon {name} not found in alignment.")
+    return [sequences[name] for name in taxon_names]
 
 
-def site_patterns_of_fasta(path, taxon_names):
-    return compress(encode(read_fasta(path), taxon_names))
+def site_patterns_of_fasta(path, taxon_names, device=0):
+    """FASTA -> (patterns [taxon][P], weights [P]); the compression runs on the
+    device (SitePattern::Compress, include/sbn_b200_patterns.h)."""
+    from .site_pattern import SitePattern
+    pattern = SitePattern(sequences_in_leaf_order(read_fasta(path), taxon_names), device)
+    return pattern.patterns, pattern.weights

@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 import libsbn  # noqa: E402  (the reference's pybind11 module)
 from libsbn_b200 import alignment  # noqa: E402
+from oracle import site_pattern  # noqa: E402
 
 
 def cpp_doubles(header, marker, occurrence=0):
@@ -72,7 +73,9 @@ def collect_gradients(gradients):
 
 def save(name, inst, fasta, spec, rooted, extra):
     inst.process_loaded_trees()  # populates taxon_names() (leaf-id order)
-    patterns, weights = alignment.site_patterns_of_fasta(fasta, inst.taxon_names())
+    # (no GPU in the build container: the NumPy restatement of SitePattern::Compress)
+    patterns, weights = site_pattern.compress(
+        alignment.sequences_in_leaf_order(alignment.read_fasta(fasta), inst.taxon_names()))
     record = {
         "patterns": patterns,
         "weights": weights,

@@ -1,0 +1,161 @@
+"""BASELINE.json's full sizes, where the CPU oracle would take minutes per tree:
+the CUDA path is held to size-independent properties of the domain, and to the
+oracle on a contiguous range of the same alignment (the engine evaluates exactly
+that range through sbnb_engine_set_pattern_range, so device offsets, tile
+boundaries and chunking are the full-size ones).
+
+  * site patterns are independent: results over pattern ranges add up to the whole;
+  * logL and every gradient are linear in the pattern weights (x2 is bit-exact);
+  * a permutation of the patterns only reorders the sums;
+  * d logL / d t agrees with central differences of logL;
+  * power-of-two rescaling does not change the result.
+"""
+import numpy as np
+import pytest
+
+import libsbn_b200 as sbn
+from libsbn_b200 import _capi, sharding, trees
+
+pytestmark = pytest.mark.gpu
+
+GTR_ROW = np.array([0.05, 0.1, 0.15, 0.20, 0.25, 0.25, 0.1, 0.2, 0.3, 0.4, 0.5])
+
+
+def raw(engine, batch, params, mode=_capi.MODE_BRANCH_GRADIENT, rescaling=True):
+    staged = engine.stage(batch, params)
+    staged.run(mode, rescaling)
+    out = staged.fetch(gradients=(mode == _capi.MODE_BRANCH_GRADIENT))
+    staged.close()
+    return out
+
+
+def alignment(taxa, patterns, seed):
+    rng = np.random.default_rng(seed)
+    states = rng.integers(0, 4, size=(taxa, patterns), dtype=np.uint8)
+    states[rng.integers(0, 100, size=(taxa, patterns), dtype=np.uint8) == 0] = 4
+    return states
+
+
+def close(a, b, rtol):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.max(np.abs(a - b)) <= rtol * np.max(np.abs(b))
+
+
+@pytest.fixture(scope="module")
+def config4():
+    """BASELINE configs[3]: 100 taxa x 100k patterns, GTR + 4 categories (3 trees)."""
+    taxa, patterns, tree_count = 100, 100000, 3
+    states = alignment(taxa, patterns, 20261017)
+    weights = np.ones(patterns)
+    parent_ids, lengths = trees.random_tree_batch(taxa, tree_count, seed=4)
+    params = np.tile(GTR_ROW, (tree_count, 1))
+    spec = sbn.PhyloModelSpecification("GTR", "weibull+4", "none")
+    engine = sbn.Engine(spec, states, weights)
+    batch = sbn.TreeBatch(parent_ids, lengths)
+    return dict(taxa=taxa, patterns=patterns, states=states, weights=weights, parent_ids=parent_ids,
+                lengths=lengths, params=params, spec=spec, engine=engine, batch=batch,
+                whole=raw(engine, batch, params))
+
+
+def test_ranges_add_up_and_match_the_oracle(oracle, config4):
+    c = config4
+    engine, batch, params = c["engine"], c["batch"], c["params"]
+    logl, grad, rgrad = c["whole"]
+    total = None
+    ranges = [sharding.pattern_range(r, 8, c["patterns"]) for r in range(8)]
+    for begin, end in ranges:
+        engine.set_pattern_range(begin, end)
+        part = raw(engine, batch, params)
+        total = [p.copy() for p in part] if total is None else [t + p for t, p in zip(total, part)]
+    assert close(total[0], logl, 1e-13) and close(total[1], grad, 1e-12) and close(total[2], rgrad, 1e-12)
+    # the oracle on one range in the middle of the alignment (not tile aligned)
+    begin, end = 61803, 62447
+    engine.set_pattern_range(begin, end)
+    got = raw(engine, batch, params)
+    engine.set_pattern_range(0, c["patterns"])
+    want = oracle.gradients("GTR", "weibull+4", c["states"][:, begin:end], c["weights"][begin:end],
+                            c["parent_ids"], c["lengths"], params, rescaling=True)
+    # raw results are in the detrifurcated tree's edge order before the root slide;
+    # compare what does not depend on that: logL, and through the public call below
+    assert close(got[0][:batch.tree_count], want["log_likelihood"], 1e-10)
+    sub = sbn.Engine(c["spec"], c["states"][:, begin:end], c["weights"][begin:end])
+    public = sub.gradients(batch, params, rescaling=True, substitution_gradient=False)
+    assert close([g.log_likelihood for g in public], want["log_likelihood"], 1e-10)
+    assert close(np.array([g.gradient["branch_lengths"] for g in public]), want["branch"], 1e-8)
+    finished = sharding.finish_gradients(c["spec"], c["taxa"], batch, False, False, got[0], got[1], got[2], 4)
+    assert close(np.array([g.gradient["branch_lengths"] for g in finished]), want["branch"], 1e-8)
+
+
+def test_linear_in_the_weights(config4):
+    c = config4
+    doubled = sbn.Engine(c["spec"], c["states"], 2.0 * c["weights"])
+    got = raw(doubled, c["batch"], c["params"])
+    for a, b in zip(got, c["whole"]):
+        assert np.array_equal(a, 2.0 * b)  # scaling by two is exact in every sum
+
+
+def test_pattern_order_does_not_matter(config4):
+    c = config4
+    order = np.random.default_rng(7).permutation(c["patterns"])
+    shuffled = sbn.Engine(c["spec"], np.ascontiguousarray(c["states"][:, order]), c["weights"][order])
+    got = raw(shuffled, c["batch"], c["params"])
+    assert close(got[0], c["whole"][0], 1e-13) and close(got[1], c["whole"][1], 1e-11)
+
+
+def test_gradient_is_the_derivative_of_the_log_likelihood(config4):
+    c = config4
+    engine, batch, params = c["engine"], c["batch"], c["params"]
+    base = engine.gradients(batch, params, rescaling=True, substitution_gradient=False)
+    rng = np.random.default_rng(3)
+    for edge in rng.choice(2 * c["taxa"] - 3, size=3, replace=False):
+        h = 1e-6
+        up, down = c["lengths"].copy(), c["lengths"].copy()
+        up[:, edge] += h
+        down[:, edge] -= h
+        f_up = engine.log_likelihoods(sbn.TreeBatch(c["parent_ids"], up), params, True)
+        f_down = engine.log_likelihoods(sbn.TreeBatch(c["parent_ids"], down), params, True)
+        numeric = (f_up - f_down) / (2 * h)
+        analytic = np.array([g.gradient["branch_lengths"][edge] for g in base])
+        noise = np.abs(f_up).max() * 1e-13 / h
+        assert np.all(np.abs(numeric - analytic) <= 1e-6 * np.abs(analytic) + 10 * noise), (edge, numeric, analytic)
+
+
+def test_rescaling_changes_nothing(config4):
+    c = config4
+    plain = raw(c["engine"], c["batch"], c["params"], rescaling=False)
+    # 100 taxa do not underflow fp64, so the unrescaled walk is valid too
+    assert close(plain[0], c["whole"][0], 1e-14) and close(plain[1], c["whole"][1], 1e-13)
+    only = raw(c["engine"], c["batch"], c["params"], mode=_capi.MODE_LOG_LIKELIHOOD)
+    assert close(only[:c["batch"].tree_count], c["whole"][0][:c["batch"].tree_count], 1e-14)
+
+
+def test_config5_shard_properties(oracle):
+    """BASELINE configs[4], one GPU's share: 1000 taxa x 125k patterns, HKY + 4
+    categories.  Ranges add up; the oracle agrees on a 300-pattern range."""
+    taxa, patterns = 1000, 125000
+    states = alignment(taxa, patterns, 5)
+    weights = np.ones(patterns)
+    parent_ids, lengths = trees.random_tree_batch(taxa, 1, seed=5)
+    params = np.array([[0.1, 0.2, 0.3, 0.4, 2.0, 0.5]])
+    spec = sbn.PhyloModelSpecification("HKY", "weibull+4", "none")
+    engine = sbn.Engine(spec, states, weights)
+    batch = sbn.TreeBatch(parent_ids, lengths)
+    whole = raw(engine, batch, params)
+    total = None
+    for r in range(3):
+        engine.set_pattern_range(*sharding.pattern_range(r, 3, patterns))
+        part = raw(engine, batch, params)
+        total = [p.copy() for p in part] if total is None else [t + p for t, p in zip(total, part)]
+    assert close(total[0], whole[0], 1e-13) and close(total[1], whole[1], 1e-12)
+    begin, end = 99991, 100291
+    sub = sbn.Engine(spec, states[:, begin:end], weights[begin:end])
+    got = sub.gradients(batch, params, rescaling=True, substitution_gradient=False)
+    raw_rates = np.array([1, 2.0, 1, 1, 2.0, 1])
+    oracle_params = np.array([list(raw_rates / raw_rates.sum()) + [0.1, 0.2, 0.3, 0.4, 0.5]])
+    want = oracle.gradients("GTR", "weibull+4", states[:, begin:end], weights[begin:end], parent_ids, lengths,
+                            oracle_params, rescaling=True)
+    assert close([g.log_likelihood for g in got], want["log_likelihood"], 1e-10)
+    assert close(np.array([g.gradient["branch_lengths"] for g in got]), want["branch"], 1e-8)
+    engine.set_pattern_range(begin, end)
+    ranged = raw(engine, batch, params)
+    assert close(ranged[0][:1], want["log_likelihood"], 1e-10)

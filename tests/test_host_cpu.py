@@ -24,7 +24,7 @@ import libsbn_b200
 
 def test_library_exports_every_declared_symbol():
     declared = set()
-    for name in ("sbn_b200.h", "sbn_b200_gp.h"):
+    for name in ("sbn_b200.h", "sbn_b200_gp.h", "sbn_b200_patterns.h"):
         header = open(os.path.join(ROOT, "include", name)).read()
         declared |= set(re.findall(r"\b(sbnb_[a-z_0-9]+)\s*\(", header))
     assert len(declared) >= 45
@@ -354,14 +354,16 @@ def test_fixture_topologies_build():
         assert sorted(post[:, 0]) == list(range(27, 53)) and slots.max() <= 5
 
 
-def test_alignment_compression_round_trip(tmp_path):
+def test_fasta_parsing_and_symbol_table(tmp_path):
     from libsbn_b200 import alignment
     path = tmp_path / "a.fasta"
-    path.write_text(">x\nACGTAC-N\n>y\nACGTACGT\n>z\naCGTAC?T\n")
-    patterns, weights = alignment.site_patterns_of_fasta(str(path), ["x", "y", "z"])
-    assert patterns.shape[0] == 3 and weights.sum() == 8
-    assert patterns.max() == 4 and set(np.unique(patterns)) <= {0, 1, 2, 3, 4}
-    # first two columns "AAA"/"CCC" then repeats of them compress
-    assert weights[0] == 2 and weights[1] == 2
+    path.write_text(">x\nACGTAC-N\n>y\nACGT\nACGT\n>z\naCGTAC?T\n")
+    sequences = alignment.read_fasta(str(path))
+    assert sequences == {"x": "ACGTAC-N", "y": "ACGTACGT", "z": "aCGTAC?T"}
+    states = alignment.encode(sequences, ["z", "x", "y"])
+    assert states.shape == (3, 8) and list(states[0]) == [0, 1, 2, 3, 0, 1, 4, 3] and states[1, 7] == 4
+    assert alignment.sequences_in_leaf_order(sequences, ["y", "x"]) == ["ACGTACGT", "ACGTAC-N"]
+    with pytest.raises(RuntimeError, match="Taxon w not found"):
+        alignment.sequences_in_leaf_order(sequences, ["w"])
     with pytest.raises(RuntimeError):
         alignment.encode({"x": "ACZT"}, ["x"])
