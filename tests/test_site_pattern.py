@@ -103,6 +103,18 @@ def test_device_matches_the_restatement(restatement, taxa, sites, distinct):
 
 
 @pytest.mark.gpu
+def test_colliding_keys_are_detected_not_merged(monkeypatch):
+    """With column keys cut to 6 bits different columns share keys under every seed:
+    the byte-for-byte verification must refuse to merge them."""
+    sequences = random_alignment(6, 2000, seed=3, distinct=500)
+    monkeypatch.setenv("SBNB_DEBUG_PATTERN_KEY_BITS", "6")
+    with pytest.raises(RuntimeError, match="collided under four seeds"):
+        SitePattern(sequences)
+    monkeypatch.setenv("SBNB_DEBUG_PATTERN_KEY_BITS", "40")  # ample: no collision among 500 columns
+    assert SitePattern(sequences).pattern_count <= 500
+
+
+@pytest.mark.gpu
 def test_device_edge_cases_and_errors(restatement):
     empty = SitePattern(["", "", ""])
     assert empty.pattern_count == 0 and empty.patterns.shape == (3, 0) and empty.weights.size == 0
