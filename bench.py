@@ -233,10 +233,13 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind
+    # Python's back (NCCL prints its version banner there in this image), so for the
+    # duration of the run descriptor 1 points at stderr and the line goes to the saved one.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own output (the version banner it
-        # prints at NCCL_DEBUG=VERSION/WARN, warnings) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -364,7 +367,8 @@ def run_ours(args):
                                                  min(args.trees, max(cores, 8)))
         line["cpu_baseline"] = dict(detail, value=cpu_value, unit=UNIT)
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -49,7 +49,9 @@ def main():
     args = parser.parse_args()
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / warnings off stdout
+    sys.stdout.flush()
+    json_fd = os.dup(1)  # NCCL prints its banner to descriptor 1: point that at stderr for the run
+    os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rank, world = dist.get_rank(), dist.get_world_size()
 
@@ -92,7 +94,7 @@ def main():
         algorithmic = (10 * n - 14) * unit_bytes * args.trees
         peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peak = json.load(open(peaks))["hbm_gbs"] if os.path.exists(peaks) else 6650.0
-        print(json.dumps({
+        line = json.dumps({
             "metric": "tree logL+branch-gradient evals/sec", "value": args.trees / seconds, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds * 1e3,
             "scaling": "strong (site patterns sharded, one NCCL all-reduce of [T] logL + [T x (2n-1)] sums)",
@@ -107,7 +109,8 @@ def main():
             "frac_of_hbm_peak_per_gpu": algorithmic / world / (kernel_ms.item() * 1e-3) / 1e9 / peak,
             "ranks_agree_bitwise": bool(same),
             "mean_log_likelihood": float(np.mean([g.log_likelihood for g in result])),
-        }))
+        })
+        os.write(json_fd, (line + "\n").encode())
     dist.destroy_process_group()
 
 
