@@ -1,6 +1,7 @@
 #!/bin/bash
-# A/B timing of tree-walk kernel variants on one GPU (development aid).
-# usage: tools/variants.sh "ENV1=a ENV2=b" "ENV1=c" ...   (one bench run per argument)
+# A/B timing of engine settings on one GPU (development aid): one short bench run per
+# argument, each argument a list of environment assignments, e.g.
+#   TREES=1024 tools/variants.sh "SBNB_TREES_IN_FLIGHT=8" "SBNB_TREES_IN_FLIGHT=64"
 mkdir -p gpurun_out
 for v in "$@"; do
   echo "== $v" | tee -a gpurun_out/variants.log
