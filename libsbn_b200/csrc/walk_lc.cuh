@@ -94,8 +94,14 @@ __device__ __forceinline__ double FastReciprocal(double x) {
 }
 
 // Per-pattern power-of-two normalisation (see Normalize in kernels.cuh) when the C
-// lanes of a pattern hold one category each.  The common case -- nothing has
-// dropped below 2^-kLazyBits -- costs a few integer max ops and one vote.
+// lanes of a pattern hold one category each: a pattern is rescaled when its largest
+// entry over all categories has dropped below 2^-kLazyBits.  Finding that maximum
+// takes shuffles, so the warp first votes on a cheaper, per-lane test with a lower
+// bar (2^-(kLazyBits + kLaneSlackBits)): a lane whose own category lags the
+// pattern's maximum by less than 2^64 does not send the warp down the slow path at
+// every op (measured: 24 % of ops took it with equal bars).  Until some lane trips
+// the vote a pattern may sit between the two bars unrescaled -- far from underflow.
+constexpr int kLaneSlackBits = 64;
 template <int C, int K>
 __device__ __forceinline__ void NormalizeLc(double (&v)[K][4], int (&exps)[K]) {
   int hi[K];
@@ -104,7 +110,7 @@ __device__ __forceinline__ void NormalizeLc(double (&v)[K][4], int (&exps)[K]) {
   for (int j = 0; j < K; j++) {
     hi[j] = max(max(__double2hiint(v[j][0]), __double2hiint(v[j][1])),
                 max(__double2hiint(v[j][2]), __double2hiint(v[j][3])));
-    low = low || (hi[j] < ((1023 - kLazyBits) << 20));
+    low = low || (hi[j] < ((1023 - kLazyBits - kLaneSlackBits) << 20));
   }
   if (!__any_sync(0xffffffffu, low)) return;
 #pragma unroll
@@ -342,27 +348,21 @@ __global__ void __launch_bounds__(kThreads, LcMinBlocks(K, GRAD)) TreeWalkLcKern
               if (RESCALE) my_stack_exps[(s0 * K + j) * kThreads] = cur_exp[j];
             }
           }
-          // At most one operand comes off the stack (the other one is cur).
-          const bool a_pop = !a_leaf && !(flags & kACur), b_pop = !b_leaf && !(flags & kBCur);
-          double x[K][4];
-          if (a_pop || b_pop) {
-            const int slot = a_pop ? s1 : s2;
+          // At most one operand comes off the stack (the other one is cur).  The pop is
+          // done inside the branch that consumes it: hoisted, its loads were predicated
+          // off but still issued at the ~75 % of ops that pop nothing.
+          int popped_exp[K];
+#pragma unroll
+          for (int j = 0; j < K; j++) popped_exp[j] = 0;
+          auto pop = [&](int slot, double (&x)[K][4]) {
 #pragma unroll
             for (int j = 0; j < K; j++) {
               const double2* src = my_stack + (static_cast<size_t>(slot) * K + j) * kRow;
               const double2 v0 = src[0], v1 = src[kThreads];
               x[j][0] = v0.x, x[j][1] = v0.y, x[j][2] = v1.x, x[j][3] = v1.y;
+              if (RESCALE) popped_exp[j] = my_stack_exps[(slot * K + j) * kThreads];
             }
-          }
-          if (RESCALE) {
-            const bool uses_cur = (flags & (kACur | kBCur)) != 0;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-              int e = uses_cur ? cur_exp[j] : 0;
-              if (a_pop || b_pop) e += my_stack_exps[((a_pop ? s1 : s2) * K + j) * kThreads];
-              cur_exp[j] = e;
-            }
-          }
+          };
           double ya[K][4], yb[K][4];
           // ---- child 0
           if (a_leaf) {
@@ -373,6 +373,8 @@ __global__ void __launch_bounds__(kThreads, LcMinBlocks(K, GRAD)) TreeWalkLcKern
             if (flags & kACur) {
               MatVecLc<K>(MA + cat * kPStride, cur, ya);
             } else {
+              double x[K][4];
+              pop(s1, x);
               MatVecLc<K>(MA + cat * kPStride, x, ya);
             }
             if (GRAD) {
@@ -393,6 +395,8 @@ __global__ void __launch_bounds__(kThreads, LcMinBlocks(K, GRAD)) TreeWalkLcKern
             if (flags & kBCur) {
               MatVecLc<K>(MB + cat * kPStride, cur, yb);
             } else {
+              double x[K][4];
+              pop(s2, x);
               MatVecLc<K>(MB + cat * kPStride, x, yb);
             }
             if (GRAD) {
@@ -403,6 +407,11 @@ __global__ void __launch_bounds__(kThreads, LcMinBlocks(K, GRAD)) TreeWalkLcKern
                 dst[j * 64 + 32] = make_double2(yb[j][2], yb[j][3]);
               }
             }
+          }
+          if (RESCALE) {
+            const bool uses_cur = (flags & (kACur | kBCur)) != 0;
+#pragma unroll
+            for (int j = 0; j < K; j++) cur_exp[j] = (uses_cur ? cur_exp[j] : 0) + popped_exp[j];
           }
 #pragma unroll
           for (int j = 0; j < K; j++)
