@@ -314,7 +314,7 @@ def run_ours(args):
     binding = max(floors_ms, key=floors_ms.get)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic_per_tree * args.trees if "hbm_real_traffic" in floors_ms else None,
-                "kernel": "TreeWalkLcKernel<C=4,K=2,GRAD,RESCALE>", "kernel_ms": kernel_ms,
+                "kernel": "TreeWalkLcKernel<C=4,K=4,GRAD,RESCALE>", "kernel_ms": kernel_ms,
                 "kernel_share_of_step": walk_ms / (ms_local if world > 1 else ms),
                 "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_source,
                 "traffic_source": f"profiles/{profile_name} (ncu --set full, dram read+write per tree x trees)",

@@ -44,8 +44,12 @@ __host__ __device__ constexpr int LcStageBytes(int C, int K) {
 }
 // Read-back slots of one pre-order op: [child][j][half][tid] double2.
 __host__ __device__ constexpr int LcScratchBytes(int K) { return 2 * K * 2 * kThreads * 16; }
+// The pre-order op works through its K patterns in sub-batches of at most 2: its
+// live set is ~5 partial-sized arrays per pattern, and K = 4 in one go needs 255
+// registers and spills.  The post-order half of the walk handles all K at once.
+__host__ __device__ constexpr int LcPreBatch(int K) { return K > 2 ? 2 : K; }
 __host__ __device__ constexpr size_t LcSmemBytes(int C, int K, bool grad) {
-  return static_cast<size_t>(kLcStages) * LcStageBytes(C, K) + 2 * kLcStages * 8 + kModelSmemDoubles * 8 + 48 +
+  return static_cast<size_t>(kLcStages) * LcStageBytes(C, K) + 2 * kLcStages * 8 + kModelSmemDoubles * 8 + 80 +
          (grad ? LcScratchBytes(K) : 0);
 }
 // Resident CTAs per SM the register allocation is held to (measured: a gradient
@@ -168,8 +172,11 @@ __global__ void __launch_bounds__(kThreads, LcMinBlocks(K, GRAD)) TreeWalkLcKern
   uint32_t* const ticket = reinterpret_cast<uint32_t*>(freqs_smem + 4);
   // Read-back slots of the current pre-order op, [child][warp][j][half][lane] double2,
   // filled per warp by bulk copies that complete on the warp's own barrier.
-  uint64_t* const readback_full = reinterpret_cast<uint64_t*>(freqs_smem + 6) + warp;
-  double2* const readback_base = reinterpret_cast<double2*>(freqs_smem + 10);
+  constexpr int KP = LcPreBatch(K);    // patterns per pre-order sub-batch ...
+  constexpr int kBatches = K / KP;     // ... and sub-batches per op, each with its own barrier
+  static_assert(K % KP == 0 && kBatches <= 2, "pre-order sub-batches must tile K");
+  uint64_t* const readback_full = reinterpret_cast<uint64_t*>(freqs_smem + 6) + warp * 2;
+  double2* const readback_base = reinterpret_cast<double2*>(freqs_smem + 14);
   constexpr int kWarpRows = K * 2 * 32;  // double2 a warp owns per node: [j][half][lane]
   const double2* const readback = readback_base + warp * kWarpRows + lane;
   if (tid == 0) {
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, LcMinBlocks(K, GRAD)) TreeWalkLcKern
       MbarInit(full + s, 1);
       MbarInit(empty + s, kWarps);
     }
-    for (int w = 0; w < kWarps; w++) MbarInit(reinterpret_cast<uint64_t*>(freqs_smem + 6) + w, 1);
+    for (int w = 0; w < 2 * kWarps; w++) MbarInit(reinterpret_cast<uint64_t*>(freqs_smem + 6) + w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -248,23 +255,24 @@ __global__ void __launch_bounds__(kThreads, LcMinBlocks(K, GRAD)) TreeWalkLcKern
       }
     };
 
-    // Lane 0 of every warp: start the bulk copies of a pre-order op's internal
-    // children's evolved partials (the warp's own arena blocks) into its read-back slots.
-    auto fetch_readback = [&](const WalkOp& op) {
+    // Lane 0 of every warp: start the bulk copies of one sub-batch of a pre-order
+    // op's internal children's evolved partials (the warp's own arena blocks) into
+    // its read-back slots.
+    auto fetch_readback = [&](const WalkOp& op, int batch) {
       const int flags = op.z >> 24;
-      constexpr uint32_t kBlockBytes = kWarpRows * 16;
+      constexpr uint32_t kBlockBytes = KP * 64 * 16;
       const uint32_t bytes = ((flags & kALeaf) ? 0 : kBlockBytes) + ((flags & kBLeaf) ? 0 : kBlockBytes);
       if (bytes == 0) {
-        MbarArrive(readback_full);
+        MbarArrive(readback_full + batch);
         return;
       }
-      MbarExpectTx(readback_full, bytes);
+      MbarExpectTx(readback_full + batch, bytes);
 #pragma unroll
       for (int child = 0; child < 2; child++) {
         if (flags & (child ? kBLeaf : kALeaf)) continue;
-        BulkCopy(readback_base + (child * kWarps + warp) * kWarpRows,
-                 my_scratch + static_cast<size_t>((child ? op.y : op.x) - n) * K * kRow, kBlockBytes,
-                 readback_full);
+        BulkCopy(readback_base + (child * kWarps + warp) * kWarpRows + batch * KP * 64,
+                 my_scratch + static_cast<size_t>((child ? op.y : op.x) - n) * K * kRow + batch * KP * 64,
+                 kBlockBytes, readback_full + batch);
       }
     };
 
@@ -437,7 +445,10 @@ __global__ void __launch_bounds__(kThreads, LcMinBlocks(K, GRAD)) TreeWalkLcKern
               // back through bulk copies (the async proxy): the first op's operands.
               asm volatile("fence.proxy.async;" ::: "memory");
               __syncwarp();
-              if (lane == 0) fetch_readback(op_next);
+              if (lane == 0) {
+#pragma unroll
+                for (int batch = 0; batch < kBatches; batch++) fetch_readback(op_next, batch);
+              }
             }
           }
         } else {
@@ -471,110 +482,116 @@ __global__ void __launch_bounds__(kThreads, LcMinBlocks(K, GRAD)) TreeWalkLcKern
             for (int j = 0; j < K; j++) ignored[j] = 0;
             NormalizeLc<C, K>(cur, ignored);  // the scale cancels in numerator / denominator
           }
-          // ---- operands: evolved partials of both children (+ Q y for tips)
-          double ya[K][4], yb[K][4];
-          double num_a[K], num_b[K];
-          MbarWait(readback_full, readback_sequence & 1);
-          readback_sequence++;
-          if (!a_leaf) {
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-              const double2 v0 = readback[j * 64], v1 = readback[j * 64 + 32];
-              ya[j][0] = v0.x, ya[j][1] = v0.y, ya[j][2] = v1.x, ya[j][3] = v1.y;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < K; j++)
-              Load4(MA + cat * kTipTableDoubles + tips_a[j * kGroup] * 4, ya[j]);
-          }
-          if (!b_leaf) {
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-              const double2 v0 = readback[kWarps * kWarpRows + j * 64], v1 = readback[kWarps * kWarpRows + j * 64 + 32];
-              yb[j][0] = v0.x, yb[j][1] = v0.y, yb[j][2] = v1.x, yb[j][3] = v1.y;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < K; j++)
-              Load4(MB + cat * kTipTableDoubles + tips_b[j * kGroup] * 4, yb[j]);
-          }
-          // the read-back slots are free again: start the next op's copies
-          __syncwarp();
-          if (lane == 0 && o + 1 < ops_total) fetch_readback(op_next);
-
-          double ta[K][4], tb[K][4], den[K];
-#pragma unroll
-          for (int j = 0; j < K; j++) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              ta[j][i] = cur[j][i] * yb[j][i];
-              tb[j][i] = cur[j][i] * ya[j][i];
-            }
-            den[j] = cat_weight * Dot4(ta[j], ya[j]);
-          }
-          // (cur is dead from here on: the kept child's pre-order partial is written into it)
-          if (a_leaf) {
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-              double da[4];
-              Load4(MA + (C + cat) * kTipTableDoubles + tips_a[j * kGroup] * 4, da);
-              num_a[j] = Dot4(ta[j], da);
-            }
-          } else {
-            MatVecDotLc<K>(q_smem, ya, ta, num_a);
-          }
-          if (b_leaf) {
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-              double db[4];
-              Load4(MB + (C + cat) * kTipTableDoubles + tips_b[j * kGroup] * 4, db);
-              num_b[j] = Dot4(tb[j], db);
-            }
-          } else {
-            MatVecDotLc<K>(q_smem, yb, tb, num_b);
-          }
-          // children's pre-order partials: one stays in cur, the other is pushed
-          if (!a_leaf) {
-            if (flags & kACur) {
-              MatTVecSharedK<K>(MA + cat * kPStride, ta, cur);
-            } else {
-              double pre[K][4];
-              MatTVecSharedK<K>(MA + cat * kPStride, ta, pre);
-#pragma unroll
-              for (int j = 0; j < K; j++) {
-                double2* dst = my_stack + (static_cast<size_t>(s1) * K + j) * kRow;
-                dst[0] = make_double2(pre[j][0], pre[j][1]);
-                dst[kThreads] = make_double2(pre[j][2], pre[j][3]);
-              }
-            }
-          }
-          if (!b_leaf) {
-            if (flags & kBCur) {
-              MatTVecSharedK<K>(MB + cat * kPStride, tb, cur);
-            } else {
-              double pre[K][4];
-              MatTVecSharedK<K>(MB + cat * kPStride, tb, pre);
-#pragma unroll
-              for (int j = 0; j < K; j++) {
-                double2* dst = my_stack + (static_cast<size_t>(s2) * K + j) * kRow;
-                dst[0] = make_double2(pre[j][0], pre[j][1]);
-                dst[kThreads] = make_double2(pre[j][2], pre[j][3]);
-              }
-            }
-          }
-
-          // ---- per-pattern ratio, then one transposed warp reduction per op
           double ga = 0.0, gb = 0.0;
 #pragma unroll
-          for (int j = 0; j < K; j++) {
-            double d = den[j];
+          for (int batch = 0; batch < kBatches; batch++) {
+            const int j0 = batch * KP;  // this sub-batch: patterns j0 .. j0 + KP - 1
+            double(&pp)[KP][4] = *reinterpret_cast<double(*)[KP][4]>(&cur[j0]);
+            // ---- operands: evolved partials of both children (+ Q y for tips)
+            double ya[KP][4], yb[KP][4];
+            double num_a[KP], num_b[KP];
+            MbarWait(readback_full + batch, readback_sequence & 1);
+            if (!a_leaf) {
 #pragma unroll
-            for (int s = kPerWarp; s < 32; s <<= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
-            // padding patterns contribute nothing (and may be 0/0)
-            const double scale = (w[j] != 0.0) ? w[j] * FastReciprocal(d) : 0.0;
-            ga = fma(scale, num_a[j], ga);
-            gb = fma(scale, num_b[j], gb);
+              for (int j = 0; j < KP; j++) {
+                const double2 v0 = readback[(j0 + j) * 64], v1 = readback[(j0 + j) * 64 + 32];
+                ya[j][0] = v0.x, ya[j][1] = v0.y, ya[j][2] = v1.x, ya[j][3] = v1.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < KP; j++)
+                Load4(MA + cat * kTipTableDoubles + tips_a[(j0 + j) * kGroup] * 4, ya[j]);
+            }
+            if (!b_leaf) {
+#pragma unroll
+              for (int j = 0; j < KP; j++) {
+                const double2 v0 = readback[kWarps * kWarpRows + (j0 + j) * 64],
+                              v1 = readback[kWarps * kWarpRows + (j0 + j) * 64 + 32];
+                yb[j][0] = v0.x, yb[j][1] = v0.y, yb[j][2] = v1.x, yb[j][3] = v1.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < KP; j++)
+                Load4(MB + cat * kTipTableDoubles + tips_b[(j0 + j) * kGroup] * 4, yb[j]);
+            }
+            // this sub-batch's read-back slots are free again: start the next op's copies
+            __syncwarp();
+            if (lane == 0 && o + 1 < ops_total) fetch_readback(op_next, batch);
+
+            double ta[KP][4], tb[KP][4], den[KP];
+#pragma unroll
+            for (int j = 0; j < KP; j++) {
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                ta[j][i] = pp[j][i] * yb[j][i];
+                tb[j][i] = pp[j][i] * ya[j][i];
+              }
+              den[j] = cat_weight * Dot4(ta[j], ya[j]);
+            }
+            // (pp is dead from here on: the kept child's pre-order partial is written into it)
+            if (a_leaf) {
+#pragma unroll
+              for (int j = 0; j < KP; j++) {
+                double da[4];
+                Load4(MA + (C + cat) * kTipTableDoubles + tips_a[(j0 + j) * kGroup] * 4, da);
+                num_a[j] = Dot4(ta[j], da);
+              }
+            } else {
+              MatVecDotLc<KP>(q_smem, ya, ta, num_a);
+            }
+            if (b_leaf) {
+#pragma unroll
+              for (int j = 0; j < KP; j++) {
+                double db[4];
+                Load4(MB + (C + cat) * kTipTableDoubles + tips_b[(j0 + j) * kGroup] * 4, db);
+                num_b[j] = Dot4(tb[j], db);
+              }
+            } else {
+              MatVecDotLc<KP>(q_smem, yb, tb, num_b);
+            }
+            // children's pre-order partials: one stays in cur, the other is pushed
+            if (!a_leaf) {
+              if (flags & kACur) {
+                MatTVecSharedK<KP>(MA + cat * kPStride, ta, pp);
+              } else {
+                double pre[KP][4];
+                MatTVecSharedK<KP>(MA + cat * kPStride, ta, pre);
+#pragma unroll
+                for (int j = 0; j < KP; j++) {
+                  double2* dst = my_stack + (static_cast<size_t>(s1) * K + j0 + j) * kRow;
+                  dst[0] = make_double2(pre[j][0], pre[j][1]);
+                  dst[kThreads] = make_double2(pre[j][2], pre[j][3]);
+                }
+              }
+            }
+            if (!b_leaf) {
+              if (flags & kBCur) {
+                MatTVecSharedK<KP>(MB + cat * kPStride, tb, pp);
+              } else {
+                double pre[KP][4];
+                MatTVecSharedK<KP>(MB + cat * kPStride, tb, pre);
+#pragma unroll
+                for (int j = 0; j < KP; j++) {
+                  double2* dst = my_stack + (static_cast<size_t>(s2) * K + j0 + j) * kRow;
+                  dst[0] = make_double2(pre[j][0], pre[j][1]);
+                  dst[kThreads] = make_double2(pre[j][2], pre[j][3]);
+                }
+              }
+            }
+            // ---- per-pattern ratio
+#pragma unroll
+            for (int j = 0; j < KP; j++) {
+              double d = den[j];
+#pragma unroll
+              for (int s = kPerWarp; s < 32; s <<= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
+              // padding patterns contribute nothing (and may be 0/0)
+              const double scale = (w[j0 + j] != 0.0) ? w[j0 + j] * FastReciprocal(d) : 0.0;
+              ga = fma(scale, num_a[j], ga);
+              gb = fma(scale, num_b[j], gb);
+            }
           }
+          readback_sequence++;
+          // ---- one transposed warp reduction per op
           // Lanes 0 / 8 / 16 / 24 end up with the warp sums of
           //   rate_w ga, rate_w gb, drate_w ga, drate_w gb.
           double v0 = rate_w * ga, v1 = rate_w * gb, v2 = drate_w * ga, v3 = drate_w * gb;
