@@ -208,15 +208,18 @@ LaunchPlan PlanAndLaunchLc(sbnb_engine* e, WalkParams p, bool launch, int chunks
   return plan;
 }
 
-template <int C, int K>
+template <int C, int K, bool GRAD>
+LaunchPlan DispatchRescale(sbnb_engine* e, const WalkParams& p, bool rescale, bool launch, int chunks_override) {
+  return rescale ? PlanAndLaunchLc<C, K, GRAD, true>(e, p, launch, chunks_override)
+                 : PlanAndLaunchLc<C, K, GRAD, false>(e, p, launch, chunks_override);
+}
+
+// K_GRAD / K_LOGL patterns per thread for the gradient / logL-only walk.
+template <int C, int K_GRAD, int K_LOGL>
 LaunchPlan DispatchModesLc(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
                            int chunks_override) {
-  if (grad) {
-    return rescale ? PlanAndLaunchLc<C, K, true, true>(e, p, launch, chunks_override)
-                   : PlanAndLaunchLc<C, K, true, false>(e, p, launch, chunks_override);
-  }
-  return rescale ? PlanAndLaunchLc<C, K, false, true>(e, p, launch, chunks_override)
-                 : PlanAndLaunchLc<C, K, false, false>(e, p, launch, chunks_override);
+  return grad ? DispatchRescale<C, K_GRAD, true>(e, p, rescale, launch, chunks_override)
+              : DispatchRescale<C, K_LOGL, false>(e, p, rescale, launch, chunks_override);
 }
 
 // Patterns per thread K: more of them amortise the per-op overhead (operand requests,
@@ -227,17 +230,15 @@ LaunchPlan Dispatch(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale
                     int chunks_override) {
   switch (e->padded_categories) {
     case 1:
-      return grad ? DispatchModesLc<1, 2>(e, p, true, rescale, launch, chunks_override)
-                  : DispatchModesLc<1, 4>(e, p, false, rescale, launch, chunks_override);
+      return DispatchModesLc<1, 2, 4>(e, p, grad, rescale, launch, chunks_override);
     case 2:
-      return grad ? DispatchModesLc<2, 2>(e, p, true, rescale, launch, chunks_override)
-                  : DispatchModesLc<2, 4>(e, p, false, rescale, launch, chunks_override);
+      return DispatchModesLc<2, 2, 4>(e, p, grad, rescale, launch, chunks_override);
     case 4:  // (measured: gradient walks with 4 patterns per thread at 2 CTAs/SM beat 2 at 3 by 3 %)
-      return DispatchModesLc<4, 4>(e, p, grad, rescale, launch, chunks_override);
+      return DispatchModesLc<4, 4, 4>(e, p, grad, rescale, launch, chunks_override);
     case 8:
-      return DispatchModesLc<8, 2>(e, p, grad, rescale, launch, chunks_override);
+      return DispatchModesLc<8, 2, 2>(e, p, grad, rescale, launch, chunks_override);
     case 16:
-      return DispatchModesLc<16, 2>(e, p, grad, rescale, launch, chunks_override);
+      return DispatchModesLc<16, 2, 2>(e, p, grad, rescale, launch, chunks_override);
   }
   Fail(SBNB_ERR_INVALID_ARGUMENT, "Unsupported category count.");
 }

@@ -1,30 +1,36 @@
-// TreeWalkLcKernel: the tree walk with LANES = (site pattern, rate category).
+// TreeWalkLcKernel: the tree walk, with LANES = (site pattern, rate category).
 //
-// Same contract as TreeWalkKernel (kernels.cuh): one pass over a tree for a tile of
-// site patterns -- post-order partial updates, per-pattern power-of-two rescaling,
-// the root log-likelihood and (gradient mode) the pre-order pass fused with all
-// edge derivatives [replaces beagleUpdatePartials, beagleUpdatePrePartials,
-// beagleCalculateEdgeDerivatives, beagleCalculateRootLogLikelihoods;
-// fat_beagle.cpp:50-70, 119-175] -- and the same programs, matrices and outputs.
+// One pass over a tree for a tile of site patterns -- post-order partial updates,
+// per-pattern power-of-two rescaling, the root log-likelihood and (gradient mode) the
+// pre-order pass fused with all edge derivatives [replaces beagleUpdatePartials,
+// beagleUpdatePrePartials, beagleCalculateEdgeDerivatives,
+// beagleCalculateRootLogLikelihoods, beagleResetScaleFactors and
+// beagleSetPartials(root pre := pi); fat_beagle.cpp:50-70, 119-175].
 //
-// What differs is the work split.  TreeWalkKernel gives a thread ALL categories of
-// its patterns and loops over them, rotating the live partial through registers;
-// that rotation and the loop's bookkeeping were ~75 % of its issued instructions.
-// Here the C lanes of a pattern each own one category:
-//   * a thread holds K patterns x 1 category x 4 states -- no category loop, no
-//     rotation, a quarter of the registers, twice the resident warps;
-//   * each lane reads ITS category's 4x4 matrix from the shared-memory operand
-//     stage (P_c blocks are padded to 18 doubles so the C lanes hit different banks);
-//   * the only cross-lane traffic is per op: the per-pattern denominator (sum over
+// Site patterns are independent, so a warp owns a tile of them and walks the WHOLE
+// tree for it.  The walk order (host-generated, Strahler-ordered, tree_program.cpp)
+// keeps the result of the previous op in registers ("cur"); only nodes with two
+// internal children touch a small thread-private stack (global memory, L2 resident).
+//
+// Work split: the C lanes of a pattern each own one category.
+//   * A thread holds K patterns x 1 category x 4 states.  (An earlier version gave a
+//     thread ALL categories of its patterns and looped over them, rotating the live
+//     partial through registers: the rotation alone was ~45 % of its instructions.)
+//   * Each lane reads ITS category's 4x4 matrix from the shared-memory operand stage.
+//     Lanes are category-major, so the 8 lanes one 128-byte wavefront serves read the
+//     same category's tables: a broadcast for a matrix, rows in different banks
+//     (picked by tip state) for a tip table.
+//   * The only cross-lane traffic is per op: the per-pattern denominator (sum over
 //     categories, a log2(C)-step butterfly), the rescaling decision (only when some
-//     lane's partial has actually dropped below 2^-128), and one 4-way transposed
-//     warp reduction of the edge-derivative sums;
-//   * the evolved post-order partials go to a thread-private arena row (coalesced
-//     16 B per lane, written once) and come back through thread-private cp.async
-//     copies issued one op ahead -- no barrier is needed for them, a thread only
-//     ever reads what it wrote itself.
-// Warps meet only at the mbarriers of the operand ring (TMA bulk copies of the two
-// child edges' matrices and the tile's tip states, issued by one elected thread).
+//     lane's partial has dropped well below 2^-128), the root's category sum, and one
+//     transposed 4-value warp reduction of the edge-derivative sums.
+//   * The evolved post-order partials y = P L go to the warp's own arena block
+//     (coalesced 16 B per lane, written once) and come back through per-warp TMA bulk
+//     copies that complete on the warp's own mbarriers -- a warp only ever reads what
+//     it wrote itself, so no CTA-wide barrier is involved.
+// Warps meet only at the mbarriers of the operand ring: TMA bulk copies of the two
+// child edges' matrix blocks and the tile's tip states, requested kLcPrefetchOps ops
+// ahead by whichever warp reaches an op first (a shared-memory ticket).
 #ifndef SBNB_WALK_LC_CUH_
 #define SBNB_WALK_LC_CUH_
 
@@ -42,7 +48,7 @@ __host__ __device__ constexpr int LcChildDoubles(int C) { return 2 * kTipTableDo
 __host__ __device__ constexpr int LcStageBytes(int C, int K) {
   return 2 * LcChildDoubles(C) * 8 + 2 * LcTipBytes(C, K);
 }
-// Read-back slots of one pre-order op: [child][j][half][tid] double2.
+// Read-back slots of one pre-order op: [child][warp][j][half][lane] double2.
 __host__ __device__ constexpr int LcScratchBytes(int K) { return 2 * K * 2 * kThreads * 16; }
 // The pre-order op works through its K patterns in sub-batches of at most 2: its
 // live set is ~5 partial-sized arrays per pattern, and K = 4 in one go needs 255
@@ -52,8 +58,8 @@ __host__ __device__ constexpr size_t LcSmemBytes(int C, int K, bool grad) {
   return static_cast<size_t>(kLcStages) * LcStageBytes(C, K) + 2 * kLcStages * 8 + kModelSmemDoubles * 8 + 80 +
          (grad ? LcScratchBytes(K) : 0);
 }
-// Resident CTAs per SM the register allocation is held to (measured: a gradient
-// walk squeezed into 128 registers spills and runs 3x slower than at 168).
+// Resident CTAs per SM the register allocation is held to.  Chosen spill-free: every
+// build with local-memory traffic in the op loop ran 2-3x slower.
 __host__ __device__ constexpr int LcMinBlocks(int K, bool grad) {
   return grad ? (K <= 2 ? 3 : 2) : (K <= 2 ? 5 : 3);
 }
