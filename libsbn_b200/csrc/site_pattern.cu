@@ -257,7 +257,7 @@ __global__ void VerifyKernel(const uint8_t* __restrict__ symbols, const uint32_t
 void Compress(int32_t n, int64_t S, const char* sequences, int32_t device, uint8_t* out_patterns,
               double* out_weights, int64_t* out_pattern_count, double* out_device_ms) {
   Require(n > 0, "Site pattern compression needs at least one sequence.");
-  Require(S >= 0 && S < (1ll << 31), "Site count out of range [0, 2^31).");
+  Require(S >= 0 && S < (1ll << 30), "Site count out of range [0, 2^30).");  // 32-bit site ids, 2S-slot table
   Require(out_pattern_count != nullptr, "out_pattern_count is NULL.");
   int device_count = 0;
   if (cudaGetDeviceCount(&device_count) != cudaSuccess || device_count == 0)
