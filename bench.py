@@ -115,6 +115,12 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- reference arm
 
+# Site patterns of the bounded CPU sample: with one tree per core this is ~40 core-seconds
+# per repeat for the reference's phylo_gradients() + log_likelihoods() pair (the cost of one
+# BranchGradientInternals is a DIFFERENCE of the two timings, so the sample must not be tiny).
+CPU_SAMPLE_PATTERNS = 10000
+
+
 def reference_throughput(args, cores, sample_patterns, sample_trees, repeats=1):
     """Times the reference's own CPU path on a bounded sample of the workload.
 
@@ -198,7 +204,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample_patterns = min(args.patterns, 2000)
+    sample_patterns = min(args.patterns, CPU_SAMPLE_PATTERNS)
     sample_trees = min(args.trees, max(cores, 8))
     for _ in range(args.warmup):
         reference_throughput(args, cores, sample_patterns, sample_trees)
@@ -363,8 +369,8 @@ def run_ours(args):
     }
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        cpu_value, detail = reference_throughput(args, cores, min(args.patterns, 2000),
-                                                 min(args.trees, max(cores, 8)))
+        cpu_value, detail = reference_throughput(args, cores, min(args.patterns, CPU_SAMPLE_PATTERNS),
+                                                 min(args.trees, max(cores, 8)), repeats=2)
         line["cpu_baseline"] = dict(detail, value=cpu_value, unit=UNIT)
     if rank == 0:
         sys.stdout.flush()
