@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsbn_b200.so")
+LIB_PATH = os.environ.get("SBNB_LIBRARY") or os.path.join(_HERE, "lib", "libsbn_b200.so")  # (override: development aid)
 
 
 class SbnbError(RuntimeError):

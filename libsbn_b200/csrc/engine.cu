@@ -21,7 +21,7 @@
 #include "common.hpp"
 #include "device_common.cuh"
 #include "kernels.cuh"
-#include "walk_lc.cuh"
+#include "walk_oe.cuh"
 #include "model.hpp"
 #include "rooted.hpp"
 #include "tree_program.hpp"
@@ -77,17 +77,29 @@ struct sbnb_engine {
   int64_t walk_samples = 0;
   int64_t launch_count = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;
-  PinnedArena staging;
+  // Page-locked staging: `staging` carries one batch to the device in one copy
+  // (staging_free is recorded behind that copy: the arena is rewritten by the next
+  // Stage, which waits for it instead of synchronising the stream); `landing`
+  // receives one batch's results in one copy.
+  PinnedArena staging, landing;
+  cudaEvent_t staging_free = nullptr;
+  bool staging_in_flight = false;
   DeviceArray<uint8_t> tips;
   DeviceArray<double> weights;
-  DeviceArray<double2> scratch;  // evolved post-order partial arena, reused by every gradient run
-  DeviceArray<double2> stack;    // per-CTA partial stacks
+  DeviceArray<double2> arena;  // evolved post-order partial arena, reused by every gradient run
+  DeviceArray<double2> stack;  // per-CTA partial stacks
   DeviceArray<int32_t> stack_exps;
+  DeviceArray<double> fd_operands;  // operand blocks of one slice of finite-difference evaluations
 
-  // A destroyed batch parks its device arrays here so the next Stage() of a
-  // same-sized collection (the one-call entry points stage per call) neither
-  // cudaMallocs nor cudaFrees (cudaFree synchronises the device).
+  // A destroyed batch parks here so that the next Stage() of the one-call entry
+  // points (which stage per call) neither cudaMallocs nor cudaFrees, and finds the
+  // traversal programs of an unchanged topology set already on the device.
   sbnb_batch* spare = nullptr;
+
+  // Multi-GPU group (sbnb_engine_create_multi): this object is then only a front
+  // for one child engine per device; see the "device groups" section below.
+  std::vector<sbnb_engine*> children;
+  int shard_axis = 0;
 
   ~sbnb_engine();
 };
@@ -97,6 +109,7 @@ struct sbnb_batch {
   int taxon_count = 0;
   int node_count = 0;  // 2n-1
   bool rooted = false;
+  bool slide_root = false;
   int fd_coords = 0;  // stick-breaking coordinates perturbed (0 if no FD staged)
   int vtree_count = 0;
   int slots = 1;
@@ -106,23 +119,44 @@ struct sbnb_batch {
   // host side, kept for the O(n) finishing steps
   std::vector<TreeProgram> programs;
   std::vector<double> lengths;  // [T][2n-1] after detrifurcation / rate scaling / root slide
-  // device side
-  DeviceArray<WalkOp> ops;  // [tree][2(n-1)]: post-order ops then pre-order ops
-  DeviceArray<int32_t> vtree_program, vtree_model, vtree_lengths;
-  DeviceArray<ModelTables> models;
-  DeviceArray<double> d_lengths, matrices;
+  // The topology set whose programs are on the device (variational inference
+  // re-evaluates the same trees with new branch lengths, vip/burrito.py:84-117).
+  std::vector<int32_t> cached_parent_ids;
+  int cached_input_nodes = 0, cached_padded_categories = 0;
+  // device side: one packed input buffer
+  //   [lengths | models | vtree_program | vtree_model | vtree_lengths]   every call
+  //   [ops | edge_offsets]                                              per topology set
+  DeviceArray<unsigned char> input;
+  size_t lengths_at = 0, models_at = 0, vtree_program_at = 0, vtree_model_at = 0, vtree_lengths_at = 0,
+         ops_at = 0, edge_offsets_at = 0;
+  int64_t post_doubles = 0, full_doubles = 0;  // operand block of a logL-only / a gradient evaluation
+  int64_t operand_stride = 0;                  // of the base trees' blocks in `operands` (last run)
+  DeviceArray<double> operands;                // operand blocks of the base trees
   DeviceArray<double> logl_partial, grad_partial, rgrad_partial;
-  DeviceArray<double> logl, grad, rgrad;
+  DeviceArray<double> results;  // [logl (vtree_count) | grad (T x N) | rgrad (T x N)]
   // tiling of the last run
   int chunks = 1;
+
+  template <typename T>
+  T* At(size_t offset) const {
+    return reinterpret_cast<T*>(input.get() + offset);
+  }
+  double* ResultLogl() const { return results.get(); }
+  double* ResultGrad() const { return results.get() + vtree_count; }
+  double* ResultRateGrad() const { return ResultGrad() + static_cast<size_t>(tree_count) * node_count; }
 };
 
 sbnb_engine::~sbnb_engine() {
+  for (sbnb_engine* child : children) {
+    cudaSetDevice(child->device);
+    delete child;
+  }
   delete spare;
   for (int i = 0; i < kWalkRing; i++) {
     if (walk_begin[i]) cudaEventDestroy(walk_begin[i]);
     if (walk_end[i]) cudaEventDestroy(walk_end[i]);
   }
+  if (staging_free) cudaEventDestroy(staging_free);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -132,8 +166,6 @@ namespace {
 void Recycle(sbnb_engine* e, sbnb_batch* batch) {
   if (!batch) return;
   if (e && !e->spare) {
-    batch->programs.clear();
-    batch->lengths.clear();
     batch->last_mode = -1;
     e->spare = batch;
   } else {
@@ -151,18 +183,26 @@ struct LaunchPlan {
   size_t smem_bytes;
 };
 
-// Plans (and launches) TreeWalkLcKernel, whose tiles are kThreads / C * K patterns.
+// Plans (and launches) TreeWalkOeKernel, whose tiles are kThreads / C * K patterns.
 template <int C, int K, bool GRAD, bool RESCALE>
-LaunchPlan PlanAndLaunchLc(sbnb_engine* e, WalkParams p, bool launch, int chunks_override) {
-  auto kernel = TreeWalkLcKernel<C, K, GRAD, RESCALE>;
-  const size_t smem = LcSmemBytes(C, K, GRAD);
-  SBNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)));
-  int per_sm = 0;
-  SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
-  if (per_sm < 1) Fail(SBNB_ERR_CUDA, "TreeWalkLcKernel does not fit on an SM.");
+LaunchPlan PlanAndLaunchOe(sbnb_engine* e, OeParams p, bool launch, int chunks_override) {
+  auto kernel = TreeWalkOeKernel<C, K, GRAD, RESCALE>;
+  // (SBNB_EXTRA_SMEM: development aid -- pads the request to lower the resident CTA count)
+  const size_t smem = OeSmemBytes(C, K, GRAD) + static_cast<size_t>(std::max(0, EnvInt("SBNB_EXTRA_SMEM", 0)));
+  static thread_local int cached_device = -1, cached_per_sm = 0;
+  static thread_local size_t cached_smem = 0;
+  if (cached_device != e->device || cached_smem != smem) {
+    SBNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SBNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, kernel, kThreads, smem));
+    cached_device = e->device;
+    cached_smem = smem;
+  }
+  const int per_sm = cached_per_sm;
+  if (per_sm < 1) Fail(SBNB_ERR_CUDA, "TreeWalkOeKernel does not fit on an SM.");
   const int resident = per_sm * e->sm_count;
-  constexpr int kTilePatterns = LcTilePatterns(C, K);
+  constexpr int kTilePatterns = OeTilePatterns(C, K);
   LaunchPlan plan;
   const int64_t patterns = p.pattern_end - p.pattern_begin;
   plan.tiles_total = static_cast<int>((patterns + kTilePatterns - 1) / kTilePatterns);
@@ -173,7 +213,7 @@ LaunchPlan PlanAndLaunchLc(sbnb_engine* e, WalkParams p, bool launch, int chunks
     // Enough (tree, chunk) work items to give every resident CTA ~4 of them, and
     // enough chunks per tree that the CTAs resident at any moment work on few
     // distinct trees: consecutive items are the chunks of one tree, and every tree
-    // in flight keeps its ~0.4 MB of transition matrices in L2 next to the arena
+    // in flight keeps its ~0.3 MB of operand blocks in L2 next to the arena
     // stream (1024 trees at 2 chunks each had 222 trees -- 81 MB -- in flight).
     int64_t want = (4LL * resident + p.vtree_count - 1) / std::max(p.vtree_count, 1);
     const int in_flight = std::max(1, EnvInt("SBNB_TREES_IN_FLIGHT", 16));
@@ -198,8 +238,8 @@ LaunchPlan PlanAndLaunchLc(sbnb_engine* e, WalkParams p, bool launch, int chunks
       p.stack_exps = e->stack_exps.get();
     }
     if (GRAD) {
-      e->scratch.Reserve(static_cast<size_t>(plan.grid) * (p.taxon_count - 1) * block);
-      p.scratch = e->scratch.get();
+      e->arena.Reserve(static_cast<size_t>(plan.grid) * std::max(p.taxon_count - 2, 1) * block);
+      p.arena = e->arena.get();
     }
     kernel<<<plan.grid, kThreads, smem, e->stream>>>(p);
     SBNB_CUDA(cudaGetLastError());
@@ -209,36 +249,36 @@ LaunchPlan PlanAndLaunchLc(sbnb_engine* e, WalkParams p, bool launch, int chunks
 }
 
 template <int C, int K, bool GRAD>
-LaunchPlan DispatchRescale(sbnb_engine* e, const WalkParams& p, bool rescale, bool launch, int chunks_override) {
-  return rescale ? PlanAndLaunchLc<C, K, GRAD, true>(e, p, launch, chunks_override)
-                 : PlanAndLaunchLc<C, K, GRAD, false>(e, p, launch, chunks_override);
+LaunchPlan DispatchRescale(sbnb_engine* e, const OeParams& p, bool rescale, bool launch, int chunks_override) {
+  return rescale ? PlanAndLaunchOe<C, K, GRAD, true>(e, p, launch, chunks_override)
+                 : PlanAndLaunchOe<C, K, GRAD, false>(e, p, launch, chunks_override);
 }
 
 // K_GRAD / K_LOGL patterns per thread for the gradient / logL-only walk.
 template <int C, int K_GRAD, int K_LOGL>
-LaunchPlan DispatchModesLc(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
+LaunchPlan DispatchModesOe(sbnb_engine* e, const OeParams& p, bool grad, bool rescale, bool launch,
                            int chunks_override) {
   return grad ? DispatchRescale<C, K_GRAD, true>(e, p, rescale, launch, chunks_override)
               : DispatchRescale<C, K_LOGL, false>(e, p, rescale, launch, chunks_override);
 }
 
 // Patterns per thread K: more of them amortise the per-op overhead (operand requests,
-// op decoding, barrier waits, reductions) but cost registers; the pre-order half of a
-// gradient walk works through them two at a time (LcPreBatch).  Tiles are
-// kThreads / C * K patterns and must stay a multiple of 16.
-LaunchPlan Dispatch(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale, bool launch,
+// barrier waits, reductions) but cost registers; the pre-order half of a gradient walk
+// works through them two at a time (OePreBatch).  Tiles are kThreads / C * K patterns
+// and must stay a multiple of 16.
+LaunchPlan Dispatch(sbnb_engine* e, const OeParams& p, bool grad, bool rescale, bool launch,
                     int chunks_override) {
   switch (e->padded_categories) {
     case 1:
-      return DispatchModesLc<1, 2, 4>(e, p, grad, rescale, launch, chunks_override);
+      return DispatchModesOe<1, 2, 4>(e, p, grad, rescale, launch, chunks_override);
     case 2:
-      return DispatchModesLc<2, 2, 4>(e, p, grad, rescale, launch, chunks_override);
-    case 4:  // (measured: gradient walks with 4 patterns per thread at 2 CTAs/SM beat 2 at 3 by 3 %)
-      return DispatchModesLc<4, 4, 4>(e, p, grad, rescale, launch, chunks_override);
+      return DispatchModesOe<2, 2, 4>(e, p, grad, rescale, launch, chunks_override);
+    case 4:
+      return DispatchModesOe<4, 4, 4>(e, p, grad, rescale, launch, chunks_override);
     case 8:
-      return DispatchModesLc<8, 2, 2>(e, p, grad, rescale, launch, chunks_override);
+      return DispatchModesOe<8, 2, 2>(e, p, grad, rescale, launch, chunks_override);
     case 16:
-      return DispatchModesLc<16, 2, 2>(e, p, grad, rescale, launch, chunks_override);
+      return DispatchModesOe<16, 2, 2>(e, p, grad, rescale, launch, chunks_override);
   }
   Fail(SBNB_ERR_INVALID_ARGUMENT, "Unsupported category count.");
 }
@@ -246,7 +286,7 @@ LaunchPlan Dispatch(sbnb_engine* e, const WalkParams& p, bool grad, bool rescale
 // (Re)builds the device copy of the alignment for patterns [begin, end): the
 // range starts at column 0 of the device arrays (TMA bulk copies need 16-byte
 // aligned rows), padded with gap states / zero weights so that the last tile
-// needs no bounds checks (a tile is at most kThreads * 2 patterns).
+// needs no bounds checks (a tile is at most kThreads * 4 patterns).
 void UploadPatternRange(sbnb_engine* e, int64_t begin, int64_t end) {
   const int64_t count = end - begin;
   e->tip_pitch = ((count + 511) / 512) * 512 + 512;
@@ -268,14 +308,13 @@ void UploadPatternRange(sbnb_engine* e, int64_t begin, int64_t end) {
 void CheckTrees(const sbnb_engine* e, const sbnb_tree_batch* trees, bool rooted) {
   Require(trees != nullptr, "NULL tree batch.");
   Require(trees->tree_count >= 0, "Negative tree count.");
-  Require(trees->tree_count == 0 || (trees->parent_ids && trees->branch_lengths),
-          "NULL parent_ids / branch_lengths.");
+  if (trees->tree_count == 0) return;  // an empty collection evaluates to an empty result
+  Require(trees->parent_ids && trees->branch_lengths, "NULL parent_ids / branch_lengths.");
   const int n = e->taxon_count;
   if (rooted) {
     Require(trees->node_count == 2 * n - 1,
             "Rooted trees must be bifurcating: node_count must be 2n-1.");
-    Require(trees->tree_count == 0 || trees->rates != nullptr,
-            "Rooted evaluation needs per-branch rates (RootedTree::rates_).");
+    Require(trees->rates != nullptr, "Rooted evaluation needs per-branch rates (RootedTree::rates_).");
   } else {
     Require(trees->node_count == 2 * n - 1 || trees->node_count == 2 * n - 2,
             "node_count must be 2n-2 (unrooted) or 2n-1 (bifurcating).");
@@ -352,7 +391,7 @@ void ParallelOverTrees(int count, F&& body) {
 // The branch lengths one evaluation of tree t uses, indexed by node id of the
 // bifurcating (2n-1 node) tree.
 void EffectiveBranchLengths(const TreeProgram& program, const sbnb_tree_batch* trees, int t, bool rooted,
-                            int N, double* out) {
+                            bool slide_root, int N, double* out) {
   const double* in = trees->branch_lengths + static_cast<size_t>(t) * trees->node_count;
   std::copy(in, in + trees->node_count, out);
   if (program.was_trifurcating) {
@@ -365,11 +404,122 @@ void EffectiveBranchLengths(const TreeProgram& program, const sbnb_tree_batch* t
     // fat_beagle.cpp:96-101, 507-511
     const double* rates = trees->rates + static_cast<size_t>(t) * (N - 1);
     for (int i = 0; i < N - 1; i++) out[i] *= rates[i];
+  } else if (slide_root) {
+    // Tree::SlideRootPosition (tree.cpp:72-78), which the reference's unrooted Gradient
+    // applies after Detrifurcate (fat_beagle.cpp:470-472): the root's second child gets
+    // length 0, its first child the sum.  A no-op for a detrifurcated tree.
+    const int fixed = program.child1[program.root], root_child = program.child0[program.root];
+    out[root_child] += out[fixed];
+    out[fixed] = 0.0;
   }
 }
 
+// Packs the two programs of one topology into the 32-byte records the kernel reads
+// from its operand-block headers, assigns every op its operand block and every edge
+// the places its matrices go, and returns the operand-block sizes (in doubles) of a
+// logL-only and of a gradient evaluation.
+//
+// The children of every op are ordered for the kernel: child a is the internal child
+// whose partial is in cur (post-order) or stays in cur (pre-order), child b the one
+// that goes through the stack -- so a tip child a implies a tip child b, and the
+// kernel has no "which child uses cur" cases.
+void PackProgram(const TreeProgram& program, int n, int C, OeOp* ops, int2* edge_offsets, int64_t* post_doubles,
+                 int64_t* full_doubles) {
+  Require(program.post_slots < 255 && program.pre_slots < 255 && 2 * n - 1 < (1 << 24), "Tree too large.");
+  auto slot_byte = [](int32_t slot) { return slot < 0 ? 0xff : (slot & 0xff); };
+  const int inner_part = kPStride * C, leaf_part = kTipTableDoubles * C;
+  for (int e = 0; e < 2 * n - 2; e++) edge_offsets[e] = make_int2(-1, -1);
+  std::vector<int32_t> arena_slot_of(2 * n - 1, 0), first_kept_child(2 * n - 1, -1);
+  int64_t at = 0;  // doubles from the block start
+  int arena_blocks = 0;
+  for (int o = 0; o < n - 1; o++) {
+    const PostOp& op = program.post[o];
+    int a = op.a, b = op.b, a_src = op.a_src, b_src = op.b_src;
+    if (b_src == kFromCur) std::swap(a, b), std::swap(a_src, b_src);
+    const bool a_leaf = a < n, b_leaf = b < n;
+    Require((a_leaf || a_src == kFromCur) && (b_leaf || b_src >= 0) && (!a_leaf || b_leaf),
+            "internal error: unexpected operand sources in a post-order op");
+    const int part_a = a_leaf ? leaf_part : inner_part, part_b = b_leaf ? leaf_part : inner_part;
+    const int flags = (a_leaf ? kALeaf : 0) | (b_leaf ? kBLeaf : 0) | (op.flags & kRoot) |
+                      (op.push_slot >= 0 ? kStackBefore : 0);
+    OeOp& out = ops[o];
+    out.operand_unit = static_cast<int32_t>(at / 2);
+    out.operand_units = (kOeHeaderDoubles + part_a + part_b) / 2;
+    out.tip_a = a_leaf ? a : -1;
+    out.tip_b = b_leaf ? b : -1;
+    out.node_flags = op.node | (flags << 24);
+    out.slots = slot_byte(op.push_slot) | (0xff << 8) | (slot_byte(b_leaf ? -1 : b_src) << 16);
+    out.arena_slot = arena_blocks;
+    out.next_arena_slot = arena_blocks;  // the root's post-order op starts its own read-back
+    arena_slot_of[op.node] = arena_blocks;
+    first_kept_child[op.node] = a;
+    arena_blocks += (a_leaf ? 0 : 1) + (b_leaf ? 0 : 1);
+    edge_offsets[a].x = static_cast<int32_t>(at + kOeHeaderDoubles);
+    edge_offsets[b].x = static_cast<int32_t>(at + kOeHeaderDoubles + part_a);
+    at += kOeHeaderDoubles + part_a + part_b;
+  }
+  *post_doubles = at;
+  auto ordered_pre = [&](const PreOp& op, int* a, int* b, int* b_dst) {
+    *a = op.a, *b = op.b;
+    int a_dst = op.a_dst;
+    *b_dst = op.b_dst;
+    if (*b_dst == kFromCur) std::swap(*a, *b), std::swap(a_dst, *b_dst);
+    const bool a_leaf = *a < n, b_leaf = *b < n;
+    Require((a_leaf || a_dst == kFromCur) && (b_leaf || *b_dst >= 0) && (!a_leaf || b_leaf),
+            "internal error: unexpected destinations in a pre-order op");
+  };
+  for (int o = 0; o < n - 1; o++) {
+    const PreOp& op = program.pre[o];
+    int a, b, b_dst;
+    ordered_pre(op, &a, &b, &b_dst);
+    const bool a_leaf = a < n, b_leaf = b < n, root = op.flags & kRoot;
+    int flags = (a_leaf ? kALeaf : 0) | (b_leaf ? kBLeaf : 0) | (op.flags & kRoot) |
+                (op.pop_slot >= 0 ? kStackBefore : 0);
+    // two internal children: their arena blocks are in the post-order op's order
+    if (!a_leaf && !b_leaf && first_kept_child[op.node] != a) flags |= kArenaSwapped;
+    OeOp& out = ops[n - 1 + o];
+    int64_t part = kOeHeaderDoubles;
+    if (!root) {
+      edge_offsets[op.node].y = static_cast<int32_t>(at + part);
+      part += inner_part;
+    }
+    if (a_leaf) {
+      edge_offsets[a].y = static_cast<int32_t>(at + part);
+      part += 2 * leaf_part;
+    }
+    if (b_leaf) {
+      edge_offsets[b].y = static_cast<int32_t>(at + part);
+      part += 2 * leaf_part;
+    }
+    out.operand_unit = static_cast<int32_t>(at / 2);
+    out.operand_units = static_cast<int32_t>(part / 2);
+    out.tip_a = a_leaf ? a : -1;
+    out.tip_b = b_leaf ? b : -1;
+    out.slots = slot_byte(op.pop_slot) | (0xff << 8) | (slot_byte(b_leaf ? -1 : b_dst) << 16);
+    out.arena_slot = arena_slot_of[op.node];
+    out.next_arena_slot = 0;
+    if (o + 1 < n - 1) {
+      const PreOp& next = program.pre[o + 1];
+      out.next_arena_slot = arena_slot_of[next.node];
+      flags |= (next.a < n ? kNextALeaf : 0) | (next.b < n ? kNextBLeaf : 0);
+    }
+    out.node_flags = op.node | (flags << 24);
+    at += part;
+  }
+  *full_doubles = at;
+  Require(at / 2 < (int64_t{1} << 31), "Tree too large.");
+}
+
+// Waits until the copy out of the staging arena that the previous Stage queued has
+// been done (normally long ago: every fetch synchronises the stream).
+void WaitForStaging(sbnb_engine* e) {
+  if (!e->staging_in_flight) return;
+  SBNB_CUDA(cudaEventSynchronize(e->staging_free));
+  e->staging_in_flight = false;
+}
+
 BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params, bool rooted,
-               bool with_fd) {
+               bool with_fd, bool slide_root) {
   CheckTrees(e, trees, rooted);
   const ModelSpec& spec = e->spec;
   Require(spec.param_count == 0 || params != nullptr || trees->tree_count == 0,
@@ -377,11 +527,13 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   SBNB_CUDA(cudaSetDevice(e->device));
   BatchPtr batch(e->spare ? e->spare : new sbnb_batch(), BatchRecycler{e});
   e->spare = nullptr;
-  const int T = trees->tree_count, n = e->taxon_count, N = 2 * n - 1;
+  const int T = trees->tree_count, n = e->taxon_count, N = 2 * n - 1, C = e->padded_categories;
+  const bool same_shape = batch->tree_count == T && batch->taxon_count == n;
   batch->tree_count = T;
   batch->taxon_count = n;
   batch->node_count = N;
   batch->rooted = rooted;
+  batch->slide_root = slide_root && !rooted;
   batch->patterns = e->range_end - e->range_begin;
   batch->categories = e->categories;
   const int fd_evals = with_fd ? 2 * spec.SubstitutionGradientSize() : 0;
@@ -389,50 +541,74 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   batch->vtree_count = T * (1 + fd_evals);
   if (T == 0) return batch;
 
-  // Everything that goes to the device is assembled in page-locked memory.
+  // Layout of the packed input buffer (identical on the host and on the device): the
+  // per-topology part first, so that its place does not depend on the model count.
   const size_t op_count = static_cast<size_t>(T) * 2 * (n - 1);
+  const size_t edge_count = static_cast<size_t>(T) * (2 * n - 2);
   const size_t max_models = static_cast<size_t>(T) * (1 + fd_evals);
-  e->staging.Reset(op_count * sizeof(WalkOp) + 3 * batch->vtree_count * sizeof(int32_t) +
-                   max_models * sizeof(ModelTables) + static_cast<size_t>(T) * N * sizeof(double) + 16 * 256);
-  WalkOp* ops = e->staging.Take<WalkOp>(op_count);
-  int32_t* vtree_program = e->staging.Take<int32_t>(batch->vtree_count);
-  int32_t* vtree_model = e->staging.Take<int32_t>(batch->vtree_count);
-  int32_t* vtree_lengths = e->staging.Take<int32_t>(batch->vtree_count);
-  ModelTables* models = e->staging.Take<ModelTables>(max_models);
-  double* lengths = e->staging.Take<double>(static_cast<size_t>(T) * N);
+  size_t at = 0;
+  auto place = [&at](size_t bytes) {
+    const size_t here = at;
+    at = (at + bytes + 255) / 256 * 256;
+    return here;
+  };
+  batch->ops_at = place(op_count * sizeof(OeOp));
+  batch->edge_offsets_at = place(edge_count * sizeof(int2));
+  const size_t per_call_begin = at;
+  batch->lengths_at = place(static_cast<size_t>(T) * N * sizeof(double));
+  batch->models_at = place(max_models * sizeof(ModelTables));
+  batch->vtree_program_at = place(batch->vtree_count * sizeof(int32_t));
+  batch->vtree_model_at = place(batch->vtree_count * sizeof(int32_t));
+  batch->vtree_lengths_at = place(batch->vtree_count * sizeof(int32_t));
+  const size_t total_bytes = at;
 
-  // Programs + branch lengths.
-  batch->programs.resize(T);
-  std::vector<int> tree_slots(T, 1);
-  ParallelOverTrees(T, [&](int t) {
-    TreeProgram program = BuildTreeProgram(
-        trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1), trees->node_count, n);
-    EffectiveBranchLengths(program, trees, t, rooted, N, lengths + static_cast<size_t>(t) * N);
-    // Pack both programs into the 16-byte records the kernel streams.
-    auto slot_byte = [](int32_t slot) { return slot < 0 ? 0xff : (slot & 0xff); };
-    Require(program.post_slots < 255 && program.pre_slots < 255 && N < (1 << 24), "Tree too large.");
-    WalkOp* tree_ops = ops + static_cast<size_t>(t) * 2 * (n - 1);
-    for (int o = 0; o < n - 1; o++) {
-      const PostOp& op = program.post[o];
-      const int post_flags = op.flags | (op.push_slot >= 0 ? kStackBefore : 0) |
-                             (op.a_src == kFromCur ? kACur : 0) | (op.b_src == kFromCur ? kBCur : 0);
-      tree_ops[o] = make_int4(op.a, op.b, op.node | (post_flags << 24),
-                              slot_byte(op.push_slot) | (slot_byte(op.a_src) << 8) | (slot_byte(op.b_src) << 16));
-      const PreOp& pre = program.pre[o];
-      const int pre_flags = pre.flags | (pre.pop_slot >= 0 ? kStackBefore : 0) |
-                            (pre.a_dst == kFromCur ? kACur : 0) | (pre.b_dst == kFromCur ? kBCur : 0);
-      tree_ops[n - 1 + o] =
-          make_int4(pre.a, pre.b, pre.node | (pre_flags << 24),
-                    slot_byte(pre.pop_slot) | (slot_byte(pre.a_dst) << 8) | (slot_byte(pre.b_dst) << 16));
-    }
-    tree_slots[t] = std::max(program.post_slots, program.pre_slots);
-    program.post.clear();
-    program.post.shrink_to_fit();
-    program.pre.clear();
-    program.pre.shrink_to_fit();
-    batch->programs[t] = std::move(program);
-  });
-  batch->slots = std::max(1, *std::max_element(tree_slots.begin(), tree_slots.end()));
+  // Is this the topology set whose programs are already on the device?
+  const size_t id_count = static_cast<size_t>(T) * (trees->node_count - 1);
+  const bool cached = same_shape && batch->cached_input_nodes == trees->node_count &&
+                      batch->cached_padded_categories == C && batch->cached_parent_ids.size() == id_count &&
+                      batch->input.capacity() >= total_bytes &&
+                      std::memcmp(batch->cached_parent_ids.data(), trees->parent_ids, id_count * sizeof(int32_t)) == 0;
+
+  // Everything that goes to the device is assembled in page-locked memory.
+  WaitForStaging(e);
+  e->staging.Reset(total_bytes);
+  unsigned char* host = e->staging.Take<unsigned char>(total_bytes);
+  double* lengths = reinterpret_cast<double*>(host + batch->lengths_at);
+  ModelTables* models = reinterpret_cast<ModelTables*>(host + batch->models_at);
+  int32_t* vtree_program = reinterpret_cast<int32_t*>(host + batch->vtree_program_at);
+  int32_t* vtree_model = reinterpret_cast<int32_t*>(host + batch->vtree_model_at);
+  int32_t* vtree_lengths = reinterpret_cast<int32_t*>(host + batch->vtree_lengths_at);
+
+  if (!cached) {
+    // Programs: host schedule generation, then the records the kernels read.
+    OeOp* ops = reinterpret_cast<OeOp*>(host + batch->ops_at);
+    int2* edge_offsets = reinterpret_cast<int2*>(host + batch->edge_offsets_at);
+    batch->programs.assign(T, TreeProgram());
+    std::vector<int> tree_slots(T, 1);
+    std::vector<int64_t> post_doubles(T), full_doubles(T);
+    ParallelOverTrees(T, [&](int t) {
+      TreeProgram program = BuildTreeProgram(
+          trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1), trees->node_count, n);
+      PackProgram(program, n, C, ops + static_cast<size_t>(t) * 2 * (n - 1),
+                  edge_offsets + static_cast<size_t>(t) * (2 * n - 2), &post_doubles[t], &full_doubles[t]);
+      tree_slots[t] = std::max(program.post_slots, program.pre_slots);
+      program.post.clear();
+      program.post.shrink_to_fit();
+      program.pre.clear();
+      program.pre.shrink_to_fit();
+      batch->programs[t] = std::move(program);
+    });
+    batch->slots = std::max(1, *std::max_element(tree_slots.begin(), tree_slots.end()));
+    // (every bifurcating tree of n taxa has n-2 internal and n tip edges: one size)
+    batch->post_doubles = post_doubles[0];
+    batch->full_doubles = full_doubles[0];
+    batch->cached_parent_ids.assign(trees->parent_ids, trees->parent_ids + id_count);
+    batch->cached_input_nodes = trees->node_count;
+    batch->cached_padded_categories = C;
+  }
+  for (int t = 0; t < T; t++)
+    EffectiveBranchLengths(batch->programs[t], trees, t, rooted, batch->slide_root, N,
+                           lengths + static_cast<size_t>(t) * N);
   batch->lengths.assign(lengths, lengths + static_cast<size_t>(T) * N);
 
   // Models: one table per distinct consecutive parameter row (+ its FD rows).
@@ -463,20 +639,17 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
     }
   }
 
+  // One copy: the per-call part alone when the programs are already there.
   cudaStream_t s = e->stream;
-  e->h2d_bytes += batch->ops.Upload(ops, op_count, s);
-  e->h2d_bytes += batch->vtree_program.Upload(vtree_program, batch->vtree_count, s);
-  e->h2d_bytes += batch->vtree_model.Upload(vtree_model, batch->vtree_count, s);
-  e->h2d_bytes += batch->vtree_lengths.Upload(vtree_lengths, batch->vtree_count, s);
-  e->h2d_bytes += batch->models.Upload(models, model_count, s);
-  e->h2d_bytes += batch->d_lengths.Upload(lengths, static_cast<size_t>(T) * N, s);
-  batch->matrices.Reserve(static_cast<size_t>(batch->vtree_count) * (N - 1) * e->padded_categories *
-                          kEdgeDoublesPerCategory);
-  batch->logl.Reserve(batch->vtree_count);
-  batch->grad.Reserve(static_cast<size_t>(T) * N);
-  batch->rgrad.Reserve(static_cast<size_t>(T) * N);
-  // The staging arena is reused by the next call.
-  SBNB_CUDA(cudaStreamSynchronize(s));
+  batch->input.Reserve(total_bytes);
+  const size_t copy_from = cached ? per_call_begin : 0;
+  SBNB_CUDA(cudaMemcpyAsync(batch->input.get() + copy_from, host + copy_from, total_bytes - copy_from,
+                            cudaMemcpyHostToDevice, s));
+  const size_t copy_bytes = total_bytes - copy_from;
+  SBNB_CUDA(cudaEventRecord(e->staging_free, s));
+  e->staging_in_flight = true;
+  e->h2d_bytes += copy_bytes;
+  batch->results.Reserve(batch->vtree_count + 2 * static_cast<size_t>(T) * N);
   return batch;
 }
 
@@ -492,21 +665,49 @@ void HarvestWalkTiming(sbnb_engine* e, int ring) {
   e->walk_pending[ring] = false;
 }
 
-WalkParams BaseParams(sbnb_engine* e, sbnb_batch* b) {
-  WalkParams p{};
+OeParams BaseParams(sbnb_engine* e, sbnb_batch* b) {
+  OeParams p{};
   p.tips = e->tips.get();
   p.tip_pitch = e->tip_pitch;
   p.weights = e->weights.get();
   p.pattern_begin = 0;  // the device arrays start at the engine's pattern range
   p.pattern_end = e->range_end - e->range_begin;
   p.taxon_count = e->taxon_count;
-  p.ops = b->ops.get();
-  p.vtree_program = b->vtree_program.get();
-  p.vtree_model = b->vtree_model.get();
-  p.models = b->models.get();
-  p.matrices = b->matrices.get();
+  p.ops = b->At<OeOp>(b->ops_at);
+  p.vtree_program = b->At<int32_t>(b->vtree_program_at);
+  p.vtree_model = b->At<int32_t>(b->vtree_model_at);
+  p.models = b->At<ModelTables>(b->models_at);
   p.slots = b->slots;
   return p;
+}
+
+// Transition matrices of virtual trees [begin, begin + count), written into the
+// operand blocks of the ops that read them, and the block headers.
+void LaunchMatrices(sbnb_engine* e, sbnb_batch* b, double* operands, int64_t stride, int begin, int count,
+                    bool with_pre) {
+  const int n = e->taxon_count, C = e->padded_categories;
+  OeMatrixParams m{};
+  m.models = b->At<ModelTables>(b->models_at);
+  m.vtree_model = b->At<int32_t>(b->vtree_model_at);
+  m.vtree_lengths = b->At<int32_t>(b->vtree_lengths_at);
+  m.vtree_program = b->At<int32_t>(b->vtree_program_at);
+  m.branch_lengths = b->At<double>(b->lengths_at);
+  m.edge_offsets = b->At<int2>(b->edge_offsets_at);
+  m.ops = b->At<OeOp>(b->ops_at);
+  m.operands = operands;
+  m.operand_stride = stride;
+  m.vtree_begin = begin;
+  m.vtree_count = count;
+  m.taxon_count = n;
+  m.categories = C;
+  m.with_pre = with_pre ? 1 : 0;
+  m.prefetch = OePrefetchOps(C);
+  const int64_t jobs = static_cast<int64_t>(count) * (2 * n - 2) * C +
+                       static_cast<int64_t>(count) * (with_pre ? 2 * (n - 1) : n - 1);
+  const int block = 128;
+  TransitionMatrixOeKernel<<<static_cast<int>((jobs + block - 1) / block), block, 0, e->stream>>>(m);
+  SBNB_CUDA(cudaGetLastError());
+  e->launch_count++;
 }
 
 void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
@@ -518,85 +719,80 @@ void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
   const int T = b->tree_count, N = b->node_count, C = e->padded_categories;
   cudaStream_t s = e->stream;
   const int vtrees = grad ? b->vtree_count : T;
+  const int fd_vtrees = vtrees - T;
 
-  // K1: transition matrices for every (virtual tree, edge, category).
-  {
-    const int64_t total = static_cast<int64_t>(vtrees) * (N - 1) * C;
-    const int block = 128;
-    const int grid = static_cast<int>((total + block - 1) / block);
-    TransitionMatrixKernel<<<grid, block, 0, s>>>(b->models.get(), b->vtree_model.get(),
-                                                  b->vtree_lengths.get(), b->d_lengths.get(),
-                                                  b->matrices.get(), vtrees, N - 1, N, C);
-    SBNB_CUDA(cudaGetLastError());
-    e->launch_count++;
-  }
+  // The finite-difference evaluations run in slices that share one operand buffer, so
+  // that memory does not grow with 1 + 2 x coordinates (17 for GTR) times the batch.
+  const int64_t slice_doubles = std::max<int64_t>(EnvInt("SBNB_FD_SLICE_MB", 1024), 1) * (1 << 20) / 8;
+  const int slice = fd_vtrees > 0
+                        ? static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(fd_vtrees, slice_doubles / b->post_doubles)))
+                        : 0;
 
-  WalkParams p = BaseParams(e, b);
-  // Base trees: logL or gradient sweep.
+  OeParams p = BaseParams(e, b);
   p.vtree_begin = 0;
   p.vtree_count = T;
   LaunchPlan plan = Dispatch(e, p, grad, rescaling, /*launch=*/false, 0);
-  const int fd_vtrees = vtrees - T;
   LaunchPlan fd_plan{};
   if (fd_vtrees > 0) {
-    WalkParams q = p;
+    OeParams q = p;
     q.vtree_begin = T;
-    q.vtree_count = fd_vtrees;
+    q.vtree_count = slice;
     fd_plan = Dispatch(e, q, false, rescaling, false, 0);
   }
-  // Partial-sum rows: [vtree][chunk][warp]; both launches share one chunk count
-  // so that a single row stride addresses the buffers.
+  // Partial-sum rows: [vtree][chunk][warp]; all launches share one chunk count so
+  // that a single row stride addresses the buffers.  Every row is written by the warp
+  // that owns it (no memset).
   const int chunks = std::max(plan.chunks, fd_vtrees > 0 ? fd_plan.chunks : 1);
   b->chunks = chunks;
   const size_t rows = static_cast<size_t>(vtrees) * chunks * kWarps;
   b->logl_partial.Reserve(rows);
-  SBNB_CUDA(cudaMemsetAsync(b->logl_partial.get(), 0, rows * sizeof(double), s));
   if (grad) {
     const size_t grad_rows = static_cast<size_t>(T) * chunks * kWarps * N;
     b->grad_partial.Reserve(grad_rows);
-    SBNB_CUDA(cudaMemsetAsync(b->grad_partial.get(), 0, grad_rows * sizeof(double), s));
-    if (C > 1) {
-      b->rgrad_partial.Reserve(grad_rows);
-      SBNB_CUDA(cudaMemsetAsync(b->rgrad_partial.get(), 0, grad_rows * sizeof(double), s));
-    }
+    if (C > 1) b->rgrad_partial.Reserve(grad_rows);
   }
   p.logl_partial = b->logl_partial.get();
   p.grad_partial = b->grad_partial.get();
   p.rgrad_partial = b->rgrad_partial.get();
+
+  // Base trees: matrices, then the logL or gradient sweep.
+  b->operand_stride = grad ? b->full_doubles : b->post_doubles;
+  b->operands.Reserve(static_cast<size_t>(T) * b->operand_stride);
+  LaunchMatrices(e, b, b->operands.get(), b->operand_stride, 0, T, grad);
+  p.operands = b->operands.get();
+  p.operand_origin = 0;
+  p.operand_stride = b->operand_stride;
   const int ring = static_cast<int>(e->walk_runs++ % sbnb_engine::kWalkRing);
   HarvestWalkTiming(e, ring);  // the slot about to be reused
   SBNB_CUDA(cudaEventRecord(e->walk_begin[ring], s));
   Dispatch(e, p, grad, rescaling, /*launch=*/true, chunks);
   SBNB_CUDA(cudaEventRecord(e->walk_end[ring], s));
   e->walk_pending[ring] = true;
+
   if (fd_vtrees > 0) {
-    WalkParams q = p;
-    q.vtree_begin = T;
-    q.vtree_count = fd_vtrees;
-    Dispatch(e, q, false, rescaling, true, chunks);
+    e->fd_operands.Reserve(static_cast<size_t>(slice) * b->post_doubles);
+    for (int begin = T; begin < vtrees; begin += slice) {
+      const int count = std::min(slice, vtrees - begin);
+      LaunchMatrices(e, b, e->fd_operands.get(), b->post_doubles, begin, count, false);
+      OeParams q = p;
+      q.vtree_begin = begin;
+      q.vtree_count = count;
+      q.operands = e->fd_operands.get();
+      q.operand_origin = begin;
+      q.operand_stride = b->post_doubles;
+      Dispatch(e, q, false, rescaling, true, chunks);
+    }
   }
 
-  // K3: fixed-order reduction of the per-(chunk, warp) partial sums.
+  // Fixed-order reduction of the per-(chunk, warp) partial sums, all arrays at once.
   {
+    const int64_t total = vtrees + (grad ? 2 * static_cast<int64_t>(T) * N : 0);
     const int block = 128;
-    ReducePartialsKernel<<<(vtrees + block - 1) / block, block, 0, s>>>(
-        b->logl_partial.get(), b->logl.get(), 0, vtrees, chunks * kWarps, 1);
+    ReduceAllKernel<<<static_cast<int>((total + block - 1) / block), block, 0, s>>>(
+        b->logl_partial.get(), b->grad_partial.get(), (grad && C > 1) ? b->rgrad_partial.get() : nullptr,
+        b->results.get(), 0, vtrees, b->vtree_count, grad ? T : 0, N, chunks * kWarps);
     SBNB_CUDA(cudaGetLastError());
     e->launch_count++;
-    if (grad) {
-      const int64_t total = static_cast<int64_t>(T) * N;
-      const int grid = static_cast<int>((total + block - 1) / block);
-      ReducePartialsKernel<<<grid, block, 0, s>>>(b->grad_partial.get(), b->grad.get(), 0, T,
-                                                  chunks * kWarps, N);
-      SBNB_CUDA(cudaGetLastError());
-      e->launch_count++;
-      if (C > 1) {
-        ReducePartialsKernel<<<grid, block, 0, s>>>(b->rgrad_partial.get(), b->rgrad.get(), 0, T,
-                                                    chunks * kWarps, N);
-        SBNB_CUDA(cudaGetLastError());
-        e->launch_count++;
-      }
-    }
   }
 }
 
@@ -604,32 +800,31 @@ void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rg
   SBNB_CUDA(cudaSetDevice(e->device));
   Require(b->last_mode >= 0, "sbnb_batch_fetch called before sbnb_batch_run.");
   const bool was_grad = (b->last_mode == SBNB_MODE_BRANCH_GRADIENT);
-  const int vtrees = was_grad ? b->vtree_count : b->tree_count;
-  const size_t per_tree = static_cast<size_t>(b->node_count);
+  Require(was_grad || (!grad && !rgrad), "No gradient available: the last run was a log-likelihood run.");
+  const size_t vtrees = was_grad ? b->vtree_count : b->tree_count;
+  const size_t grad_count = static_cast<size_t>(b->tree_count) * b->node_count;
   cudaStream_t s = e->stream;
   if (b->tree_count > 0) {
-    if (logl) {
-      SBNB_CUDA(cudaMemcpyAsync(logl, b->logl.get(), vtrees * sizeof(double), cudaMemcpyDeviceToHost, s));
-      e->d2h_bytes += vtrees * sizeof(double);
-    }
-    if (grad) {
-      Require(was_grad, "No gradient available: the last run was a log-likelihood run.");
-      SBNB_CUDA(cudaMemcpyAsync(grad, b->grad.get(), b->tree_count * per_tree * sizeof(double),
-                                cudaMemcpyDeviceToHost, s));
-      e->d2h_bytes += b->tree_count * per_tree * sizeof(double);
-    }
+    // One copy of what is asked for into page-locked memory, then out to the caller's arrays.
+    const bool rates = rgrad && e->padded_categories > 1;
+    const size_t count = (grad || rates) ? b->vtree_count + (rates ? 2 : 1) * grad_count : vtrees;
+    e->landing.Reset(count * sizeof(double));
+    double* landed = e->landing.Take<double>(count);
+    SBNB_CUDA(cudaMemcpyAsync(landed, b->results.get(), count * sizeof(double), cudaMemcpyDeviceToHost, s));
+    e->d2h_bytes += count * sizeof(double);
+    SBNB_CUDA(cudaStreamSynchronize(s));
+    if (logl) std::copy(landed, landed + vtrees, logl);
+    if (grad) std::copy(landed + b->vtree_count, landed + b->vtree_count + grad_count, grad);
     if (rgrad) {
-      Require(was_grad, "No gradient available: the last run was a log-likelihood run.");
-      if (e->padded_categories > 1) {
-        SBNB_CUDA(cudaMemcpyAsync(rgrad, b->rgrad.get(), b->tree_count * per_tree * sizeof(double),
-                                  cudaMemcpyDeviceToHost, s));
-        e->d2h_bytes += b->tree_count * per_tree * sizeof(double);
+      if (rates) {
+        std::copy(landed + b->vtree_count + grad_count, landed + b->vtree_count + 2 * grad_count, rgrad);
       } else {
-        std::fill(rgrad, rgrad + b->tree_count * per_tree, 0.0);
+        std::fill(rgrad, rgrad + grad_count, 0.0);
       }
     }
+  } else {
+    SBNB_CUDA(cudaStreamSynchronize(s));
   }
-  SBNB_CUDA(cudaStreamSynchronize(s));
 }
 
 RootedView ViewOf(const sbnb_tree_batch* trees, int t, int n) {
@@ -648,8 +843,9 @@ RootedView ViewOf(const sbnb_tree_batch* trees, int t, int n) {
 // The one-call forms of Engine's five methods.
 void LogLikelihoods(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params,
                     bool rescaling, bool rooted_semantics, bool add_jacobian, double* out) {
+  Require(trees != nullptr, "NULL tree batch.");
   Require(out != nullptr || trees->tree_count == 0, "NULL output.");
-  auto batch = Stage(e, trees, params, rooted_semantics, false);
+  auto batch = Stage(e, trees, params, rooted_semantics, false, /*slide_root=*/false);
   Run(e, batch.get(), SBNB_MODE_LOG_LIKELIHOOD, rescaling);
   Fetch(e, batch.get(), out, nullptr, nullptr);
   if (add_jacobian) {
@@ -669,6 +865,7 @@ void LogLikelihoods(sbnb_engine* e, const sbnb_tree_batch* trees, const double* 
 void FinishGradients(const ModelSpec& spec, int n, const sbnb_tree_batch* trees, bool rooted, int fd_coords,
                      const double* logl, const double* grad, const double* rgrad,
                      const sbnb_gradient_out* out, const std::vector<TreeProgram>* programs = nullptr) {
+  Require(trees != nullptr, "NULL tree batch.");
   Require(out != nullptr, "NULL gradient output.");
   const int T = trees->tree_count, N = 2 * n - 1;
   if (rooted)
@@ -692,7 +889,7 @@ void FinishGradients(const ModelSpec& spec, int n, const sbnb_tree_batch* trees,
             (fd[2 * k] - fd[2 * k + 1]) / (2. * kFiniteDifferenceDelta);
     }
     if (out->site_model && categories > 1) {
-      EffectiveBranchLengths(tree, trees, t, rooted, N, lengths.data());
+      EffectiveBranchLengths(tree, trees, t, rooted, /*slide_root=*/true, N, lengths.data());
       out->site_model[t] =
           DiscreteSiteModelGradient(N, lengths.data(), rgrad + static_cast<size_t>(t) * N);  // fat_beagle.cpp:389-398
     }
@@ -717,8 +914,10 @@ void FinishGradients(const ModelSpec& spec, int n, const sbnb_tree_batch* trees,
 void Gradients(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params, bool rescaling,
                bool rooted, const sbnb_gradient_out* out) {
   Require(out != nullptr, "NULL gradient output.");
+  Require(trees != nullptr, "NULL tree batch.");
   const int fd_coords = e->spec.SubstitutionGradientSize();
-  auto batch = Stage(e, trees, params, rooted, fd_coords > 0 && out->substitution_model != nullptr);
+  auto batch = Stage(e, trees, params, rooted, fd_coords > 0 && out->substitution_model != nullptr,
+                     /*slide_root=*/true);
   Run(e, batch.get(), SBNB_MODE_BRANCH_GRADIENT, rescaling);
   const int T = trees->tree_count, N = 2 * e->taxon_count - 1;
   std::vector<double> logl(batch->vtree_count), grad(static_cast<size_t>(T) * N),
@@ -775,6 +974,7 @@ int sbnb_engine_create(const char* substitution, const char* site, const char* c
     engine->padded_categories = PadCategories(engine->categories);
     Require(engine->padded_categories > 0, "At most 16 rate categories are supported.");
     SBNB_CUDA(cudaStreamCreateWithFlags(&engine->stream, cudaStreamNonBlocking));
+    SBNB_CUDA(cudaEventCreateWithFlags(&engine->staging_free, cudaEventDisableTiming));
     for (int i = 0; i < sbnb_engine::kWalkRing; i++) {
       SBNB_CUDA(cudaEventCreate(&engine->walk_begin[i]));
       SBNB_CUDA(cudaEventCreate(&engine->walk_end[i]));
@@ -899,8 +1099,11 @@ int sbnb_batch_stage(sbnb_engine* engine, const sbnb_tree_batch* trees, const do
   return Guard([&] {
     Require(engine && out, "NULL argument.");
     *out = nullptr;
+    // (unrooted batches are staged with the root slid as the reference's Gradient does:
+    //  a no-op for trifurcating input; for bifurcating input the log-likelihood is the
+    //  same by the pulley principle)
     *out = Stage(engine, trees, params, (stage_flags & SBNB_STAGE_ROOTED) != 0,
-                 (stage_flags & SBNB_STAGE_SUBSTITUTION_FD) != 0)
+                 (stage_flags & SBNB_STAGE_SUBSTITUTION_FD) != 0, /*slide_root=*/true)
                .release();
   });
 }
@@ -924,9 +1127,10 @@ int sbnb_batch_device_results(sbnb_batch* batch, void** log_likelihoods, void** 
                               void** rate_gradients) {
   return Guard([&] {
     Require(batch != nullptr, "NULL batch.");
-    if (log_likelihoods) *log_likelihoods = batch->logl.get();
-    if (branch_gradients) *branch_gradients = batch->grad.get();
-    if (rate_gradients) *rate_gradients = batch->rgrad.get();
+    // (one contiguous fp64 array: log-likelihoods, branch gradients, rate gradients)
+    if (log_likelihoods) *log_likelihoods = batch->ResultLogl();
+    if (branch_gradients) *branch_gradients = batch->ResultGrad();
+    if (rate_gradients) *rate_gradients = batch->categories > 1 ? batch->ResultRateGrad() : nullptr;
   });
 }
 
