@@ -479,10 +479,8 @@ void PackProgram(const TreeProgram& program, int n, int C, OeOp* ops, int2* edge
     if (!a_leaf && !b_leaf && first_kept_child[op.node] != a) flags |= kArenaSwapped;
     OeOp& out = ops[n - 1 + o];
     int64_t part = kOeHeaderDoubles;
-    if (!root) {
-      edge_offsets[op.node].y = static_cast<int32_t>(at + part);
-      part += inner_part;
-    }
+    if (!root) edge_offsets[op.node].y = static_cast<int32_t>(at + part);
+    part += inner_part;  // (the root's op gets an identity there)
     if (a_leaf) {
       edge_offsets[a].y = static_cast<int32_t>(at + part);
       part += 2 * leaf_part;

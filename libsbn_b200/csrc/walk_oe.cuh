@@ -71,7 +71,7 @@ enum : int32_t { kArenaSwapped = 16, kNextALeaf = 64, kNextBLeaf = 128 };
 //   [0, 8)    header: the op's own record, then the record of the op kOePrefetchOps ahead
 //   post-order op:  child a part, child b part; a part is P_c row-major, 18 doubles
 //                   apart (internal child) or per c: P_c^T + a row of ones (tip child)
-//   pre-order op:   own P (18 C, absent at the root), then per TIP child 40 C:
+//   pre-order op:   own P (18 C; an identity at the root), then per TIP child 40 C:
 //                   per c P_c^T + ones, per c (Q P_c)^T + zeros
 constexpr int kOeHeaderDoubles = 8;
 __host__ __device__ constexpr int OeMaxOperandDoubles(int C) {
@@ -146,8 +146,18 @@ __global__ void TransitionMatrixOeKernel(const OeMatrixParams p) {
                                             static_cast<int64_t>(program[o].operand_unit) * 2);
     header[0] = own[0];
     header[1] = own[1];
-    header[2] = ahead[0];
+    int4 request = ahead[0];
+    // how many tiles further on the op kOePrefetchOps ahead is (bits 16.. of the size word)
+    request.y |= ((o + p.prefetch) / ops_used) << 16;
+    header[2] = request;
     header[3] = ahead[1];
+    if ((static_cast<unsigned>(program[o].node_flags) >> 24) & kRoot && o >= n - 1) {
+      // The root has no edge: its pre-order op multiplies by an identity "P", so that
+      // the kernel needs no root case (pp = I^T pi).
+      double* identity = reinterpret_cast<double*>(header) + kOeHeaderDoubles;
+      for (int c = 0; c < C; c++)
+        for (int k = 0; k < kPStride; k++) identity[c * kPStride + k] = (k < 16 && k % 5 == 0) ? 1.0 : 0.0;
+    }
     return;
   }
   const int c = static_cast<int>(idx % C);
@@ -315,10 +325,15 @@ __device__ __forceinline__ double FastReciprocalOe(double x) {
 // whose own category lags the pattern's maximum by less than 2^64 does not send the
 // warp down the slow path at every op.  Until some lane trips the vote a pattern may
 // sit between the two bars unrescaled -- far from underflow.
-//   Post-order partials use BAR = 128 (their product is taken next); pre-order
-// partials, whose scale cancels in numerator / denominator and which lose ~2^-100 per
-// level (the sibling's evolved partial), use BAR = 384: the slow path then runs every
-// few levels instead of at (measured) 96 % of the pre-order ops.
+//   Post-order partials are rescaled with BAR = kOeLazyBits = 32.  The pre-order partial
+// pp at a node satisfies sum_c pp_c . L_c = the pattern's (scaled) root likelihood over
+// the factors the node's ancestors' own rescalings applied: with every scaled L inside
+// [2^-32, 1] it moves only when an ancestor was rescaled, so the pre-order pass tests the
+// already reduced pp . L against 2^-kOePreBits -- one vote per sub-batch and a slow path
+// that practically only deep trees take (with the 2^-128 bar of the previous kernels pp
+// lost ~2^-100 per level and 96 % of the pre-order ops went down a shuffle-based slow path).
+constexpr int kOeLazyBits = 32;
+constexpr int kOePreBits = 384;
 constexpr int kOeLaneSlackBits = 64;
 template <int C, int K, int BAR>
 __device__ __forceinline__ void NormalizeOe(double (&v)[K][4], int (&exps)[K]) {
@@ -430,8 +445,8 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
     if (tid < 16) {
       q_smem[tid] = model.q[tid];
       cat_weight_smem[tid] = model.weights[tid];
-      rate_weight_smem[tid] = model.weights[tid] * model.rates[tid];    // p_c r_c
-      drate_weight_smem[tid] = model.weights[tid] * model.drates[tid];  // p_c dr_c/dshape
+      rate_weight_smem[tid] = model.rates[tid];    // r_c  (p_c rides in the pre-order partials)
+      drate_weight_smem[tid] = model.drates[tid];  // dr_c/dshape
       if (tid < 4) freqs_smem[tid] = model.freqs[tid];
     }
     if (GRAD) {
@@ -452,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
       const int s = seq % kStages;
       if (seq >= kStages) MbarWait(empty + s, ((seq / kStages) - 1) & 1);
       unsigned char* stage = ring + s * kStage;
-      const uint32_t operand_bytes = static_cast<uint32_t>(record.y) * 16;
+      const uint32_t operand_bytes = static_cast<uint32_t>(record.y & 0xffff) * 16;
       const uint32_t bytes = operand_bytes + (record.z >= 0 ? kTipBytes : 0) + (record.w >= 0 ? kTipBytes : 0);
       MbarExpectTx(full + s, bytes);
       BulkCopy(stage, block + static_cast<int64_t>(record.x) * 2, operand_bytes, full + s);
@@ -494,8 +509,6 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
     const double cat_weight = cat_weight_smem[cat];
     const double rate_w = rate_weight_smem[cat];
     const double drate_w = drate_weight_smem[cat];
-    int ahead_o = kPrefetch % ops_total;                  // op g + kPrefetch: index within its tile ...
-    int ahead_tile = tile_begin + kPrefetch / ops_total;  // ... and the tile
     int g = 0;
 
     double logl_acc = 0.0;
@@ -530,10 +543,12 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
           // (plain read first: only a warp that can win goes through the atomic)
           if (*reinterpret_cast<volatile uint32_t*>(ticket) == target &&
               atomicCAS(ticket, target, target + 1) == target)
-            issue(target, *reinterpret_cast<const int4*>(stage + 32),
-                  p.pattern_begin + static_cast<int64_t>(ahead_tile) * kTilePatterns);
+          {
+            // the record of op g + kPrefetch, and how many tiles further on it is
+            const int4 request = *reinterpret_cast<const int4*>(stage + 32);
+            issue(target, request, pat0 + static_cast<int64_t>(request.y >> 16) * kTilePatterns);
+          }
         }
-        if (++ahead_o == ops_total) ahead_o = 0, ahead_tile++;
         __syncwarp();
         const double* const operand = reinterpret_cast<const double*>(stage) + kOeHeaderDoubles;
         const uint8_t* const tips_a = stage + kOperandBytes + pidx;
@@ -607,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
           for (int j = 0; j < K; j++)
 #pragma unroll
             for (int i = 0; i < 4; i++) cur[j][i] = ya[j][i] * yb[j][i];
-          if (RESCALE) NormalizeOe<C, K, kLazyBits>(cur, cur_exp);
+          if (RESCALE) NormalizeOe<C, K, kOeLazyBits>(cur, cur_exp);
           if (flags & kRoot) {
             // beagleCalculateRootLogLikelihoods: log sum_c p_c sum_i pi_i L[c,k,i] (+ scale)
             double freqs[4];
@@ -623,8 +638,16 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
               logl_acc = fma(w[j], (w[j] != 0.0 && cat == 0) ? log_site : 0.0, logl_acc);
             }
             if (GRAD) {
-              // The pre-order pass reads the arena back through bulk copies (the async
-              // proxy), which was written with ordinary stores: the root's own blocks first.
+              // The pre-order pass starts at the root with T = p_c pi (its operand block
+              // holds an identity in the place of the root's P).  Carrying the category
+              // proportion in the pre-order partials makes pp . L the category's share of
+              // the site likelihood and every numerator already weighted by p_c.
+#pragma unroll
+              for (int j = 0; j < K; j++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) cur[j][i] = cat_weight * freqs[i];
+              // It reads the arena back through bulk copies (the async proxy), which was
+              // written with ordinary stores: the root's own blocks first.
               asm volatile("fence.proxy.async;" ::: "memory");
               __syncwarp();
               if (lane == 0) {
@@ -635,9 +658,8 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
           }
         } else {
           // ================ pre-order op + edge derivatives ================
-          const bool root = flags & kRoot;
-          // operand layout: own P (absent at the root), tip tables of a, tip tables of b
-          const double* const table_a = operand + (root ? 0 : kInnerPart);
+          // operand layout: own P (an identity at the root), tip tables of a, tip tables of b
+          const double* const table_a = operand + kInnerPart;
           const double* const table_b = table_a + (a_leaf ? 2 * kLeafPart : 0);
           const int next_children = ((flags & kNextALeaf) ? 0 : 1) + ((flags & kNextBLeaf) ? 0 : 1);
           // read-back order of two internal children: the post-order op's child order
@@ -647,16 +669,9 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
           for (int batch = 0; batch < kBatches; batch++) {
             const int j0 = batch * KP;  // this sub-batch: patterns j0 .. j0 + KP - 1
             double(&top)[KP][4] = *reinterpret_cast<double(*)[KP][4]>(&cur[j0]);
-            // ---- pre-order partial at this node: pp = P^T T (root: pi)
+            // ---- pre-order partial at this node: pp = P^T T
             double pp[KP][4];
-            if (root) {
-              double freqs[4];
-              Load4(freqs_smem, freqs);
-#pragma unroll
-              for (int j = 0; j < KP; j++)
-#pragma unroll
-                for (int i = 0; i < 4; i++) pp[j][i] = freqs[i];
-            } else if (flags & kStackBefore) {
+            if (flags & kStackBefore) {
               const int s0 = record.y & 0xff;
               double x[KP][4];
 #pragma unroll
@@ -668,12 +683,6 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
               MatTVecSharedK<KP>(operand + cat * kPStride, x, pp);
             } else {
               MatTVecSharedK<KP>(operand + cat * kPStride, top, pp);
-            }
-            if (RESCALE) {
-              int ignored[KP];
-#pragma unroll
-              for (int j = 0; j < KP; j++) ignored[j] = 0;
-              NormalizeOe<C, KP, 384>(pp, ignored);  // the scale cancels in numerator / denominator
             }
             // ---- evolved partials of both children
             double ya[KP][4], yb[KP][4];
@@ -709,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
             for (int j = 0; j < KP; j++) {
 #pragma unroll
               for (int i = 0; i < 4; i++) site[j][i] = ya[j][i] * yb[j][i];
-              double d = cat_weight * Dot4(pp[j], site[j]);
+              double d = Dot4(pp[j], site[j]);
 #pragma unroll
               for (int s = kPerWarp; s < 32; s <<= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
               // padding patterns contribute nothing (and may be 0/0)
@@ -727,8 +736,8 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
             // the loads have been performed: the copy is issued behind that dependency.
             if (lane == 0 && o + 1 < ops_total) fetch_readback(record.w, next_children, batch);
 
-            // ---- own edge: T^T Q P L = pp . (Q L)
-            if (!root) {
+            // ---- own edge: T^T Q P L = pp . (Q L)   (computed and dropped at the root)
+            {
               double num[KP];
               MatVecDotOe<KP>(q_smem, site, pp, num);
 #pragma unroll
@@ -748,6 +757,31 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
                 double d[4];
                 Load4(table_a + (C + cat) * kTipTableDoubles + tips_a[(j0 + j) * kGroup] * 4, d);
                 g_a = fma(scale[j], Dot4(top[j], d), g_a);
+              }
+            }
+            if (RESCALE) {
+              // pp . L is the pattern's root likelihood divided by the scale factors its
+              // ancestors' own rescalings applied, so down a deep tree it shrinks (a
+              // 1000-taxon ladder underflows without this).  All lanes of a pattern hold
+              // the same reduced value: when it has dropped below 2^-kOePreBits the
+              // partials handed down are scaled by its inverse power of two -- the scale
+              // cancels in every numerator / denominator below.  Rare: one vote per batch.
+              // (tested on scale = weight / (pp . L), whose power of two serves as the factor)
+              bool low = false;
+#pragma unroll
+              for (int j = 0; j < KP; j++) low = low || (__double2hiint(scale[j]) > ((1023 + kOePreBits) << 20));
+              if (__any_sync(0xffffffffu, low)) {
+#pragma unroll
+                for (int j = 0; j < KP; j++) {
+                  const int biased = (__double2hiint(scale[j]) >> 20) & 0x7ff;
+                  if (biased <= 1023 + kOePreBits || biased == 0x7ff) continue;
+                  const double boost = __hiloint2double(biased << 20, 0);
+#pragma unroll
+                  for (int i = 0; i < 4; i++) {
+                    top[j][i] *= boost;               // T_a (dead if a is a tip: its term is in g_a already)
+                    if (!b_leaf) yb[j][i] *= boost;   // T_b, pushed below (a tip's term uses it as is)
+                  }
+                }
               }
             }
             if (b_leaf) {
@@ -800,7 +834,7 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
               const int which = (lane >> 2) & 3;  // 0 own edge, 1 tip child a, 2 tip child b
               const int2 tip_ids = *reinterpret_cast<const int2*>(stage + 8);
               int edge = -1;
-              if (which == 0) edge = root ? -1 : (record.x & 0xffffff);
+              if (which == 0) edge = (flags & kRoot) ? -1 : (record.x & 0xffffff);
               if (which == 1) edge = a_leaf ? tip_ids.x : -1;
               if (which == 2) edge = b_leaf ? tip_ids.y : -1;
               if (edge >= 0) {
