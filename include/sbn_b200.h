@@ -71,6 +71,29 @@ int sbnb_engine_create(const char* substitution, const char* site, const char* c
                        const double* pattern_weights, int32_t device, sbnb_engine** out);
 void sbnb_engine_destroy(sbnb_engine* engine);
 
+/*
+ * A device group: one engine over several GPUs of the box, replacing the
+ * reference's thread_count FatBeagle instances and the thread pool that fans a
+ * collection over them (engine.cpp:17-27, fat_beagle.hpp:119-149) -- one host thread
+ * and one stream per device inside the library.  `devices` lists CUDA ordinals
+ * (an ordinal may repeat).  shard_axis:
+ *   SBNB_SHARD_TREES     every device evaluates a contiguous slice of the collection
+ *                        (trees are independent; no exchange step);
+ *   SBNB_SHARD_PATTERNS  every device walks all trees over its range of site patterns
+ *                        and the raw per-tree sums are added across devices over
+ *                        NVLink peer memory before one host finishing (for a tree
+ *                        whose partials one device should not hold alone).
+ * A group offers the one-call entry points (sbnb_log_likelihoods_*, sbnb_gradients_*);
+ * the staged entry points below work on single-device engines.
+ */
+enum { SBNB_SHARD_TREES = 0, SBNB_SHARD_PATTERNS = 1 };
+int sbnb_engine_create_multi(const char* substitution, const char* site, const char* clock,
+                             int32_t taxon_count, int64_t pattern_count, const uint8_t* tip_states,
+                             const double* pattern_weights, const int32_t* devices,
+                             int32_t device_count, int32_t shard_axis, sbnb_engine** out);
+/* Number of devices behind an engine (1 unless created with sbnb_engine_create_multi). */
+int32_t sbnb_engine_device_count(const sbnb_engine* engine);
+
 /* Engine::GetPhyloModelBlockSpecification (engine.hpp:31): total parameter
  * count K of one row, and (start, length) of a named block such as
  * "GTR rates", "frequencies", "kappa", "Weibull shape", "Gamma shape", "clock rate", "entire

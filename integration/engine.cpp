@@ -9,6 +9,8 @@
 #include "engine.hpp"
 
 #include <algorithm>
+#include <cstdlib>
+#include <sstream>
 #include <string>
 
 #include "sbn_b200.h"
@@ -141,10 +143,44 @@ Engine::Engine(const EngineSpecification &engine_specification,
           static_cast<uint8_t>((symbol < 0 || symbol > 4) ? 4 : symbol);
     }
   }
-  Check(sbnb_engine_create(specification.substitution_.c_str(), specification.site_.c_str(),
-                           specification.clock_.c_str(), static_cast<int32_t>(taxon_count),
-                           static_cast<int64_t>(pattern_count), tip_states.data(),
-                           site_pattern_.GetWeights().data(), /*device=*/0, &device_engine_));
+  // thread_count_ was the number of BEAGLE instances the reference fanned a collection
+  // over (engine.cpp:17-27); here it is the number of GPUs: the first
+  // min(thread_count_, visible devices) ordinals, or the list in SBNB_DEVICES
+  // ("0,2,3").  One device -> a plain engine; several -> a device group inside
+  // libsbn_b200.so (one host thread + stream per GPU), sharded by tree, or by site
+  // pattern with SBNB_SHARD_AXIS=patterns.
+  std::vector<int32_t> devices;
+  if (const char *list = std::getenv("SBNB_DEVICES")) {
+    std::stringstream stream(list);
+    std::string item;
+    while (std::getline(stream, item, ',')) {
+      if (!item.empty()) devices.push_back(static_cast<int32_t>(std::stoi(item)));
+    }
+  } else {
+    const size_t visible = static_cast<size_t>(std::max(sbnb_device_count(), 1));
+    for (size_t device = 0; device < std::min(engine_specification.thread_count_, visible);
+         device++) {
+      devices.push_back(static_cast<int32_t>(device));
+    }
+  }
+  if (devices.empty()) {
+    Failwith("SBNB_DEVICES names no CUDA device.");
+  }
+  const char *axis = std::getenv("SBNB_SHARD_AXIS");
+  const bool by_pattern = axis != nullptr && std::string(axis) == "patterns";
+  if (devices.size() == 1) {
+    Check(sbnb_engine_create(specification.substitution_.c_str(), specification.site_.c_str(),
+                             specification.clock_.c_str(), static_cast<int32_t>(taxon_count),
+                             static_cast<int64_t>(pattern_count), tip_states.data(),
+                             site_pattern_.GetWeights().data(), devices[0], &device_engine_));
+  } else {
+    Check(sbnb_engine_create_multi(
+        specification.substitution_.c_str(), specification.site_.c_str(),
+        specification.clock_.c_str(), static_cast<int32_t>(taxon_count),
+        static_cast<int64_t>(pattern_count), tip_states.data(), site_pattern_.GetWeights().data(),
+        devices.data(), static_cast<int32_t>(devices.size()),
+        by_pattern ? SBNB_SHARD_PATTERNS : SBNB_SHARD_TREES, &device_engine_));
+  }
   Assert(static_cast<size_t>(sbnb_engine_param_count(device_engine_)) ==
              phylo_model_->GetBlockSpecification().ParameterCount(),
          "The device engine and PhyloModel disagree about the parameter count.");

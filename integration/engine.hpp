@@ -27,9 +27,10 @@
 struct sbnb_engine;
 
 // Same three fields as the reference (generic_sbn_instance.hpp:252 brace-initialises
-// it).  thread_count_ and the BEAGLE flags are accepted and ignored: one CUDA device
-// evaluates the whole collection in one launch; use_tip_states_ selects between two
-// BEAGLE code paths with identical results, of which the device has only one.
+// it).  thread_count_ -- the reference's number of BEAGLE instances -- is the number of
+// GPUs the collection is fanned over (engine.cpp); the BEAGLE flags are accepted and
+// ignored; use_tip_states_ selects between two BEAGLE code paths with identical results,
+// of which the device has only one.
 struct EngineSpecification {
   const size_t thread_count_;
   const std::vector<BeagleFlags> &beagle_flag_vector_;

@@ -55,6 +55,10 @@ SIGNATURES = {
     "sbnb_device_count": (_c.c_int, []),
     "sbnb_engine_create": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int32, _c.c_int64,
                                       _P(_c.c_uint8), _P(_c.c_double), _c.c_int32, _P(_c.c_void_p)]),
+    "sbnb_engine_create_multi": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int32, _c.c_int64,
+                                            _P(_c.c_uint8), _P(_c.c_double), _P(_c.c_int32), _c.c_int32,
+                                            _c.c_int32, _P(_c.c_void_p)]),
+    "sbnb_engine_device_count": (_c.c_int32, [_c.c_void_p]),
     "sbnb_engine_destroy": (None, [_c.c_void_p]),
     "sbnb_engine_param_count": (_c.c_int32, [_c.c_void_p]),
     "sbnb_engine_param_block": (_c.c_int, [_c.c_void_p, _c.c_char_p, _P(_c.c_int32), _P(_c.c_int32)]),
@@ -128,6 +132,8 @@ MODE_LOG_LIKELIHOOD = 0
 MODE_BRANCH_GRADIENT = 1
 STAGE_ROOTED = 1
 STAGE_SUBSTITUTION_FD = 2
+SHARD_TREES = 0
+SHARD_PATTERNS = 1
 
 _lib = None
 

@@ -64,8 +64,9 @@ struct sbnb_engine {
   int64_t range_begin = 0, range_end = 0;
   int categories = 1;         // C
   int padded_categories = 1;  // instantiated count >= C (extra categories have weight 0)
-  std::vector<uint8_t> host_tips;    // [taxon][pattern], states clamped to 0..4
-  std::vector<double> host_weights;  // [pattern]
+  // host copy of the alignment (shared by the children of a device group)
+  std::shared_ptr<const std::vector<uint8_t>> host_tips;    // [taxon][pattern], states clamped to 0..4
+  std::shared_ptr<const std::vector<double>> host_weights;  // [pattern]
   cudaStream_t stream = nullptr;
   // CUDA-event pairs bracketing the base tree-walk launch of the last
   // kWalkRing runs; harvested into (walk_total_ms, walk_samples).
@@ -292,11 +293,11 @@ void UploadPatternRange(sbnb_engine* e, int64_t begin, int64_t end) {
   e->tip_pitch = ((count + 511) / 512) * 512 + 512;
   std::vector<uint8_t> tips(static_cast<size_t>(e->taxon_count) * e->tip_pitch, 4);
   for (int taxon = 0; taxon < e->taxon_count; taxon++)
-    std::copy(e->host_tips.begin() + static_cast<size_t>(taxon) * e->pattern_count + begin,
-              e->host_tips.begin() + static_cast<size_t>(taxon) * e->pattern_count + end,
+    std::copy(e->host_tips->begin() + static_cast<size_t>(taxon) * e->pattern_count + begin,
+              e->host_tips->begin() + static_cast<size_t>(taxon) * e->pattern_count + end,
               tips.begin() + static_cast<size_t>(taxon) * e->tip_pitch);
   std::vector<double> weights(e->tip_pitch, 0.0);
-  std::copy(e->host_weights.begin() + begin, e->host_weights.begin() + end, weights.begin());
+  std::copy(e->host_weights->begin() + begin, e->host_weights->begin() + end, weights.begin());
   SBNB_CUDA(cudaStreamSynchronize(e->stream));  // nothing in flight reads the old arrays
   e->h2d_bytes += e->tips.Upload(tips.data(), tips.size(), e->stream);
   e->h2d_bytes += e->weights.Upload(weights.data(), weights.size(), e->stream);
@@ -838,6 +839,55 @@ RootedView ViewOf(const sbnb_tree_batch* trees, int t, int n) {
   return view;
 }
 
+// Engine::Engine + FatBeagle::FatBeagle for one device.  `sibling` (a child of the same
+// device group) shares its host copy of the alignment.
+std::unique_ptr<sbnb_engine> CreateEngine(const char* substitution, const char* site, const char* clock,
+                                          int32_t taxon_count, int64_t pattern_count, const uint8_t* tip_states,
+                                          const double* pattern_weights, int32_t device,
+                                          const sbnb_engine* sibling) {
+  Require(substitution && site && clock, "NULL model specification string.");
+  Require(taxon_count >= 2, "Need at least 2 taxa.");
+  Require(pattern_count >= 1, "Need at least 1 site pattern.");
+  Require(tip_states && pattern_weights, "NULL tip_states / pattern_weights.");
+  auto engine = std::make_unique<sbnb_engine>();
+  engine->spec = ModelSpec::Parse(substitution, site, clock);
+  int device_count = 0;
+  if (cudaGetDeviceCount(&device_count) != cudaSuccess || device_count < 1) {
+    cudaGetLastError();
+    Fail(SBNB_ERR_NO_DEVICE, "No CUDA device available: libsbn_b200 has no CPU fallback (cudaGetDeviceCount).");
+  }
+  Require(device >= 0 && device < device_count, "CUDA device ordinal out of range.");
+  SBNB_CUDA(cudaSetDevice(device));
+  engine->device = device;
+  int sm_count = 0;
+  SBNB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  engine->sm_count = sm_count;
+  engine->taxon_count = taxon_count;
+  engine->pattern_count = pattern_count;
+  engine->range_begin = 0;
+  engine->range_end = pattern_count;
+  engine->categories = engine->spec.category_count;
+  engine->padded_categories = PadCategories(engine->categories);
+  Require(engine->padded_categories > 0, "At most 16 rate categories are supported.");
+  SBNB_CUDA(cudaStreamCreateWithFlags(&engine->stream, cudaStreamNonBlocking));
+  SBNB_CUDA(cudaEventCreateWithFlags(&engine->staging_free, cudaEventDisableTiming));
+  for (int i = 0; i < sbnb_engine::kWalkRing; i++) {
+    SBNB_CUDA(cudaEventCreate(&engine->walk_begin[i]));
+    SBNB_CUDA(cudaEventCreate(&engine->walk_end[i]));
+  }
+  if (sibling) {
+    engine->host_tips = sibling->host_tips;
+    engine->host_weights = sibling->host_weights;
+  } else {
+    auto tips = std::make_shared<std::vector<uint8_t>>(static_cast<size_t>(taxon_count) * pattern_count);
+    for (size_t i = 0; i < tips->size(); i++) (*tips)[i] = tip_states[i] < 4 ? tip_states[i] : 4;
+    engine->host_tips = tips;
+    engine->host_weights = std::make_shared<std::vector<double>>(pattern_weights, pattern_weights + pattern_count);
+  }
+  UploadPatternRange(engine.get(), 0, pattern_count);
+  return engine;
+}
+
 // The one-call forms of Engine's five methods.
 void LogLikelihoods(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params,
                     bool rescaling, bool rooted_semantics, bool add_jacobian, double* out) {
@@ -925,6 +975,189 @@ void Gradients(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
                   rgrad.data(), out, &batch->programs);
 }
 
+
+// ---------------------------------------------------------------------------
+// Device groups (sbnb_engine_create_multi): the reference's Engine owns
+// thread_count FatBeagles and fans a collection over them (engine.cpp:23-27,
+// fat_beagle.hpp:119-149); here a group owns one child engine per GPU, one host
+// thread + stream each, and the two shard axes of SURVEY.md 8e:
+//   trees    -- child g evaluates a contiguous slice of the collection and writes its
+//               rows of the caller's output arrays; no exchange step.
+//   patterns -- every child walks ALL trees over its range of site patterns; the raw
+//               per-tree sums (log-likelihoods, edge derivatives) of children 1.. are
+//               added onto child 0's result array by PeerSumKernel, which reads the
+//               peers' device memory directly over NVLink (or staged peer copies when
+//               peer access is unavailable), in a fixed order; then one fetch and one
+//               host finishing.
+
+// One host thread per child; the first failure is rethrown on the calling thread.
+template <typename F>
+void ParallelOverChildren(sbnb_engine* group, F&& body) {
+  const int G = static_cast<int>(group->children.size());
+  std::vector<std::thread> threads;
+  std::exception_ptr failure;
+  std::mutex failure_mutex;
+  for (int g = 0; g < G; g++) {
+    threads.emplace_back([&, g] {
+      try {
+        FloatingPointEnvironmentKeeper keep_environment;
+        body(g, group->children[g]);
+      } catch (...) {
+        std::lock_guard<std::mutex> lock(failure_mutex);
+        if (!failure) failure = std::current_exception();
+      }
+    });
+  }
+  for (auto& thread : threads) thread.join();
+  if (failure) std::rethrow_exception(failure);
+}
+
+// The trees [begin, end) of a batch as a batch of their own.
+sbnb_tree_batch SliceTrees(const sbnb_tree_batch* trees, int n, int begin, int end) {
+  sbnb_tree_batch slice = *trees;
+  slice.tree_count = end - begin;
+  const size_t nodes = trees->node_count;
+  auto advance = [begin](const auto* base, size_t stride) { return base ? base + begin * stride : base; };
+  slice.parent_ids = advance(trees->parent_ids, nodes - 1);
+  slice.branch_lengths = advance(trees->branch_lengths, nodes);
+  slice.rates = advance(trees->rates, nodes - 1);
+  slice.node_heights = advance(trees->node_heights, nodes);
+  slice.node_bounds = advance(trees->node_bounds, nodes);
+  slice.height_ratios = advance(trees->height_ratios, static_cast<size_t>(n - 1));
+  return slice;
+}
+
+// Pattern axis: stage + run on every child, sum the raw results onto child 0.
+// Returns child 0's batch (results complete once its stream has been synchronised).
+std::vector<BatchPtr> RunOverPatternShards(sbnb_engine* group, const sbnb_tree_batch* trees, const double* params,
+                                           bool rooted, bool with_fd, bool slide_root, int mode, bool rescaling) {
+  const int G = static_cast<int>(group->children.size());
+  std::vector<BatchPtr> batches;
+  for (int g = 0; g < G; g++) batches.emplace_back(nullptr, BatchRecycler{group->children[g]});
+  std::vector<cudaEvent_t> done(G, nullptr);
+  ParallelOverChildren(group, [&](int g, sbnb_engine* child) {
+    batches[g] = Stage(child, trees, params, rooted, with_fd, slide_root);
+    Run(child, batches[g].get(), mode, rescaling);
+    if (g > 0) {
+      SBNB_CUDA(cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming));
+      SBNB_CUDA(cudaEventRecord(done[g], child->stream));
+    }
+  });
+  sbnb_engine* first = group->children[0];
+  sbnb_batch* b0 = batches[0].get();
+  if (trees->tree_count > 0 && G > 1) {
+    SBNB_CUDA(cudaSetDevice(first->device));
+    const bool grad = (mode == SBNB_MODE_BRANCH_GRADIENT);
+    const int64_t count =
+        grad ? b0->vtree_count + (first->padded_categories > 1 ? 2 : 1) * static_cast<int64_t>(b0->tree_count) * b0->node_count
+             : b0->tree_count;
+    PeerPointers peers{};
+    peers.part[0] = b0->results.get();
+    for (int g = 1; g < G; g++) {
+      sbnb_engine* child = group->children[g];
+      SBNB_CUDA(cudaStreamWaitEvent(first->stream, done[g], 0));
+      int can_access = (child->device == first->device) ? 1 : 0;
+      if (!can_access) {
+        SBNB_CUDA(cudaDeviceCanAccessPeer(&can_access, first->device, child->device));
+        if (can_access) {
+          const cudaError_t status = cudaDeviceEnablePeerAccess(child->device, 0);
+          if (status == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+          else if (status != cudaSuccess) can_access = 0, cudaGetLastError();
+        }
+      }
+      if (can_access) {
+        peers.part[g] = batches[g]->results.get();  // read in place, over NVLink
+      } else {
+        first->fd_operands.Reserve(static_cast<size_t>(count) * G);  // (free between runs) staging for peer copies
+        double* staged = first->fd_operands.get() + static_cast<size_t>(count) * g;
+        SBNB_CUDA(cudaMemcpyPeerAsync(staged, first->device, batches[g]->results.get(), child->device,
+                                      count * sizeof(double), first->stream));
+        peers.part[g] = staged;
+      }
+    }
+    const int block = 256;
+    PeerSumKernel<<<static_cast<int>((count + block - 1) / block), block, 0, first->stream>>>(
+        b0->results.get(), peers, G, count);
+    SBNB_CUDA(cudaGetLastError());
+    first->launch_count++;
+  }
+  // The children's result arrays must outlive the sum: wait for it here.
+  SBNB_CUDA(cudaSetDevice(first->device));
+  SBNB_CUDA(cudaStreamSynchronize(first->stream));
+  for (int g = 1; g < G; g++)
+    if (done[g]) cudaEventDestroy(done[g]);
+  return batches;
+}
+
+void GroupLogLikelihoods(sbnb_engine* group, const sbnb_tree_batch* trees, const double* params, bool rescaling,
+                         bool rooted_semantics, bool add_jacobian, double* out) {
+  Require(trees != nullptr, "NULL tree batch.");
+  Require(out != nullptr || trees->tree_count == 0, "NULL output.");
+  const int G = static_cast<int>(group->children.size()), T = trees->tree_count, n = group->taxon_count;
+  const int K = group->spec.param_count;
+  if (group->shard_axis == SBNB_SHARD_TREES) {
+    ParallelOverChildren(group, [&](int g, sbnb_engine* child) {
+      const int begin = static_cast<int>(static_cast<int64_t>(T) * g / G);
+      const int end = static_cast<int>(static_cast<int64_t>(T) * (g + 1) / G);
+      if (begin == end) return;
+      const sbnb_tree_batch slice = SliceTrees(trees, n, begin, end);
+      LogLikelihoods(child, &slice, params ? params + static_cast<size_t>(begin) * K : nullptr, rescaling,
+                     rooted_semantics, add_jacobian, out + begin);
+    });
+    return;
+  }
+  auto batches = RunOverPatternShards(group, trees, params, rooted_semantics, false, false,
+                                      SBNB_MODE_LOG_LIKELIHOOD, rescaling);
+  Fetch(group->children[0], batches[0].get(), out, nullptr, nullptr);
+  if (add_jacobian) {
+    Require(T == 0 || (trees->node_heights && trees->node_bounds),
+            "Rooted log likelihoods need node_heights and node_bounds.");
+    for (int t = 0; t < T; t++) out[t] += LogDetJacobianHeightRatios(batches[0]->programs[t], ViewOf(trees, t, n));
+  }
+}
+
+void GroupGradients(sbnb_engine* group, const sbnb_tree_batch* trees, const double* params, bool rescaling,
+                    bool rooted, const sbnb_gradient_out* out) {
+  Require(out != nullptr, "NULL gradient output.");
+  Require(trees != nullptr, "NULL tree batch.");
+  const int G = static_cast<int>(group->children.size()), T = trees->tree_count, n = group->taxon_count;
+  const int N = 2 * n - 1, K = group->spec.param_count;
+  const int fd_coords = group->spec.SubstitutionGradientSize();
+  if (group->shard_axis == SBNB_SHARD_TREES) {
+    ParallelOverChildren(group, [&](int g, sbnb_engine* child) {
+      const int begin = static_cast<int>(static_cast<int64_t>(T) * g / G);
+      const int end = static_cast<int>(static_cast<int64_t>(T) * (g + 1) / G);
+      if (begin == end) return;
+      const sbnb_tree_batch slice = SliceTrees(trees, n, begin, end);
+      sbnb_gradient_out rows = *out;
+      auto advance = [begin](double* base, size_t width) { return base ? base + begin * width : base; };
+      rows.log_likelihood = advance(out->log_likelihood, 1);
+      rows.branch_lengths = advance(out->branch_lengths, N);
+      rows.substitution_model = advance(out->substitution_model, fd_coords);
+      rows.site_model = advance(out->site_model, 1);
+      rows.ratios_root_height = advance(out->ratios_root_height, n - 1);
+      rows.clock_model = advance(out->clock_model, std::max(trees->rate_count, 0));
+      Gradients(child, &slice, params ? params + static_cast<size_t>(begin) * K : nullptr, rescaling, rooted,
+                &rows);
+    });
+    return;
+  }
+  auto batches = RunOverPatternShards(group, trees, params, rooted,
+                                      fd_coords > 0 && out->substitution_model != nullptr, true,
+                                      SBNB_MODE_BRANCH_GRADIENT, rescaling);
+  sbnb_batch* b0 = batches[0].get();
+  std::vector<double> logl(b0->vtree_count), grad(static_cast<size_t>(T) * N), rgrad(static_cast<size_t>(T) * N);
+  Fetch(group->children[0], b0, logl.data(), grad.data(), rgrad.data());
+  FinishGradients(group->spec, n, trees, rooted, b0->fd_coords, logl.data(), grad.data(), rgrad.data(), out,
+                  &b0->programs);
+}
+
+bool IsGroup(const sbnb_engine* e) { return !e->children.empty(); }
+void RequireSingleDevice(const sbnb_engine* e) {
+  Require(!IsGroup(e), "The staged entry points work on one device: call them on an engine created with "
+                       "sbnb_engine_create (a device group offers the one-call entry points).");
+}
+
 }  // namespace
 
 extern "C" {
@@ -946,44 +1179,46 @@ int sbnb_engine_create(const char* substitution, const char* site, const char* c
   return Guard([&] {
     Require(out != nullptr, "NULL output handle.");
     *out = nullptr;
-    Require(substitution && site && clock, "NULL model specification string.");
-    Require(taxon_count >= 2, "Need at least 2 taxa.");
-    Require(pattern_count >= 1, "Need at least 1 site pattern.");
-    Require(tip_states && pattern_weights, "NULL tip_states / pattern_weights.");
-    auto engine = std::make_unique<sbnb_engine>();
-    engine->spec = ModelSpec::Parse(substitution, site, clock);
-    int device_count = 0;
-    if (cudaGetDeviceCount(&device_count) != cudaSuccess || device_count < 1) {
-      cudaGetLastError();
-      Fail(SBNB_ERR_NO_DEVICE,
-           "No CUDA device available: libsbn_b200 has no CPU fallback (cudaGetDeviceCount).");
-    }
-    Require(device >= 0 && device < device_count, "CUDA device ordinal out of range.");
-    SBNB_CUDA(cudaSetDevice(device));
-    engine->device = device;
-    cudaDeviceProp prop{};
-    SBNB_CUDA(cudaGetDeviceProperties(&prop, device));
-    engine->sm_count = prop.multiProcessorCount;
-    engine->taxon_count = taxon_count;
-    engine->pattern_count = pattern_count;
-    engine->range_begin = 0;
-    engine->range_end = pattern_count;
-    engine->categories = engine->spec.category_count;
-    engine->padded_categories = PadCategories(engine->categories);
-    Require(engine->padded_categories > 0, "At most 16 rate categories are supported.");
-    SBNB_CUDA(cudaStreamCreateWithFlags(&engine->stream, cudaStreamNonBlocking));
-    SBNB_CUDA(cudaEventCreateWithFlags(&engine->staging_free, cudaEventDisableTiming));
-    for (int i = 0; i < sbnb_engine::kWalkRing; i++) {
-      SBNB_CUDA(cudaEventCreate(&engine->walk_begin[i]));
-      SBNB_CUDA(cudaEventCreate(&engine->walk_end[i]));
-    }
-    engine->host_tips.resize(static_cast<size_t>(taxon_count) * pattern_count);
-    for (size_t i = 0; i < engine->host_tips.size(); i++)
-      engine->host_tips[i] = tip_states[i] < 4 ? tip_states[i] : 4;
-    engine->host_weights.assign(pattern_weights, pattern_weights + pattern_count);
-    UploadPatternRange(engine.get(), 0, pattern_count);
-    *out = engine.release();
+    *out = CreateEngine(substitution, site, clock, taxon_count, pattern_count, tip_states, pattern_weights, device,
+                        nullptr)
+               .release();
   });
+}
+
+int sbnb_engine_create_multi(const char* substitution, const char* site, const char* clock,
+                             int32_t taxon_count, int64_t pattern_count, const uint8_t* tip_states,
+                             const double* pattern_weights, const int32_t* devices, int32_t device_count,
+                             int32_t shard_axis, sbnb_engine** out) {
+  return Guard([&] {
+    Require(out != nullptr, "NULL output handle.");
+    *out = nullptr;
+    Require(devices != nullptr && device_count >= 1 && device_count <= 16, "Need 1 to 16 device ordinals.");
+    Require(shard_axis == SBNB_SHARD_TREES || shard_axis == SBNB_SHARD_PATTERNS, "Unknown shard axis.");
+    Require(shard_axis == SBNB_SHARD_TREES || pattern_count >= device_count,
+            "Cannot shard fewer site patterns than devices.");
+    auto group = std::make_unique<sbnb_engine>();
+    group->shard_axis = shard_axis;
+    for (int g = 0; g < device_count; g++) {
+      auto child = CreateEngine(substitution, site, clock, taxon_count, pattern_count, tip_states, pattern_weights,
+                                devices[g], group->children.empty() ? nullptr : group->children[0]);
+      if (shard_axis == SBNB_SHARD_PATTERNS && device_count > 1)
+        UploadPatternRange(child.get(), pattern_count * g / device_count, pattern_count * (g + 1) / device_count);
+      group->children.push_back(child.release());
+    }
+    const sbnb_engine* first = group->children[0];
+    group->spec = first->spec;
+    group->device = first->device;
+    group->taxon_count = first->taxon_count;
+    group->pattern_count = first->pattern_count;
+    group->categories = first->categories;
+    group->padded_categories = first->padded_categories;
+    *out = group.release();
+  });
+}
+
+int32_t sbnb_engine_device_count(const sbnb_engine* engine) {
+  if (!engine) return -1;
+  return engine->children.empty() ? 1 : static_cast<int32_t>(engine->children.size());
 }
 
 void sbnb_engine_destroy(sbnb_engine* engine) {
@@ -1015,7 +1250,7 @@ int sbnb_log_likelihoods_unrooted(sbnb_engine* engine, const sbnb_tree_batch* tr
                                   const double* params, int32_t rescaling, double* out) {
   return Guard([&] {
     Require(engine != nullptr, "NULL engine.");
-    LogLikelihoods(engine, trees, params, rescaling != 0, false, false, out);
+    (IsGroup(engine) ? GroupLogLikelihoods : LogLikelihoods)(engine, trees, params, rescaling != 0, false, false, out);
   });
 }
 
@@ -1023,7 +1258,7 @@ int sbnb_log_likelihoods_rooted(sbnb_engine* engine, const sbnb_tree_batch* tree
                                 const double* params, int32_t rescaling, double* out) {
   return Guard([&] {
     Require(engine != nullptr, "NULL engine.");
-    LogLikelihoods(engine, trees, params, rescaling != 0, true, true, out);
+    (IsGroup(engine) ? GroupLogLikelihoods : LogLikelihoods)(engine, trees, params, rescaling != 0, true, true, out);
   });
 }
 
@@ -1034,7 +1269,7 @@ int sbnb_unrooted_log_likelihoods_of_rooted(sbnb_engine* engine, const sbnb_tree
     // fat_beagle.cpp:78-80: plain branch lengths, no rates, no Jacobian.
     Require(trees && trees->node_count == 2 * engine->taxon_count - 1,
             "Rooted trees must be bifurcating: node_count must be 2n-1.");
-    LogLikelihoods(engine, trees, params, rescaling != 0, false, false, out);
+    (IsGroup(engine) ? GroupLogLikelihoods : LogLikelihoods)(engine, trees, params, rescaling != 0, false, false, out);
   });
 }
 
@@ -1042,7 +1277,7 @@ int sbnb_gradients_unrooted(sbnb_engine* engine, const sbnb_tree_batch* trees, c
                             int32_t rescaling, const sbnb_gradient_out* out) {
   return Guard([&] {
     Require(engine != nullptr, "NULL engine.");
-    Gradients(engine, trees, params, rescaling != 0, false, out);
+    (IsGroup(engine) ? GroupGradients : Gradients)(engine, trees, params, rescaling != 0, false, out);
   });
 }
 
@@ -1050,7 +1285,7 @@ int sbnb_gradients_rooted(sbnb_engine* engine, const sbnb_tree_batch* trees, con
                           int32_t rescaling, const sbnb_gradient_out* out) {
   return Guard([&] {
     Require(engine != nullptr, "NULL engine.");
-    Gradients(engine, trees, params, rescaling != 0, true, out);
+    (IsGroup(engine) ? GroupGradients : Gradients)(engine, trees, params, rescaling != 0, true, out);
   });
 }
 
@@ -1097,6 +1332,7 @@ int sbnb_batch_stage(sbnb_engine* engine, const sbnb_tree_batch* trees, const do
   return Guard([&] {
     Require(engine && out, "NULL argument.");
     *out = nullptr;
+    RequireSingleDevice(engine);
     // (unrooted batches are staged with the root slid as the reference's Gradient does:
     //  a no-op for trifurcating input; for bifurcating input the log-likelihood is the
     //  same by the pulley principle)
@@ -1109,6 +1345,7 @@ int sbnb_batch_stage(sbnb_engine* engine, const sbnb_tree_batch* trees, const do
 int sbnb_batch_run(sbnb_engine* engine, sbnb_batch* batch, int32_t mode, int32_t rescaling) {
   return Guard([&] {
     Require(engine && batch, "NULL argument.");
+    RequireSingleDevice(engine);
     Run(engine, batch, mode, rescaling != 0);
   });
 }
@@ -1117,6 +1354,7 @@ int sbnb_batch_fetch(sbnb_engine* engine, sbnb_batch* batch, double* log_likelih
                      double* branch_gradients, double* rate_gradients) {
   return Guard([&] {
     Require(engine && batch, "NULL argument.");
+    RequireSingleDevice(engine);
     Fetch(engine, batch, log_likelihoods, branch_gradients, rate_gradients);
   });
 }
@@ -1143,10 +1381,16 @@ int32_t sbnb_batch_evaluation_count(const sbnb_batch* batch) {
   return batch->last_mode == SBNB_MODE_BRANCH_GRADIENT ? batch->vtree_count : batch->tree_count;
 }
 
-void* sbnb_engine_stream(sbnb_engine* engine) { return engine ? engine->stream : nullptr; }
+void* sbnb_engine_stream(sbnb_engine* engine) {
+  if (!engine) return nullptr;
+  return IsGroup(engine) ? engine->children[0]->stream : engine->stream;
+}
 
 int64_t sbnb_engine_launch_count(const sbnb_engine* engine) {
-  return engine ? engine->launch_count : -1;
+  if (!engine) return -1;
+  int64_t count = engine->launch_count;
+  for (const sbnb_engine* child : engine->children) count += child->launch_count;
+  return count;
 }
 
 int sbnb_engine_transfer_bytes(const sbnb_engine* engine, int64_t* host_to_device,
@@ -1155,6 +1399,10 @@ int sbnb_engine_transfer_bytes(const sbnb_engine* engine, int64_t* host_to_devic
     Require(engine && host_to_device && device_to_host, "NULL argument.");
     *host_to_device = engine->h2d_bytes;
     *device_to_host = engine->d2h_bytes;
+    for (const sbnb_engine* child : engine->children) {
+      *host_to_device += child->h2d_bytes;
+      *device_to_host += child->d2h_bytes;
+    }
   });
 }
 
@@ -1162,6 +1410,7 @@ int sbnb_engine_walk_timing(sbnb_engine* engine, double* total_ms, int64_t* samp
                             int32_t reset) {
   return Guard([&] {
     Require(engine && total_ms && samples, "NULL argument.");
+    RequireSingleDevice(engine);
     SBNB_CUDA(cudaSetDevice(engine->device));
     // oldest first, so that walk_last_ms ends up being the newest run
     for (int i = 0; i < sbnb_engine::kWalkRing; i++)
@@ -1187,6 +1436,7 @@ double sbnb_batch_algorithmic_bytes(const sbnb_batch* batch, int32_t mode) {
 int sbnb_engine_set_pattern_range(sbnb_engine* engine, int64_t begin, int64_t end) {
   return Guard([&] {
     Require(engine != nullptr, "NULL engine.");
+    RequireSingleDevice(engine);
     Require(0 <= begin && begin < end && end <= engine->pattern_count,
             "Pattern range must satisfy 0 <= begin < end <= pattern_count.");
     SBNB_CUDA(cudaSetDevice(engine->device));

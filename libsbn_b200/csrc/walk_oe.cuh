@@ -258,6 +258,22 @@ __global__ void ReduceAllKernel(const double* __restrict__ logl_partial, const d
   dst[k] = sum;
 }
 
+// Device groups sharded by site pattern (engine.cu): the raw per-tree sums of the other
+// devices, read through peer pointers over NVLink, are added onto this device's array.
+struct PeerPointers {
+  const double* part[16];
+};
+
+// out[i] += part[1][i] + part[2][i] + ... in a fixed order (part[0] is out itself).
+__global__ void PeerSumKernel(double* __restrict__ out, PeerPointers peers, int32_t count_of_peers, int64_t count) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double sum = out[i];
+  for (int g = 1; g < count_of_peers; g++) sum += peers.part[g][i];
+  out[i] = sum;
+}
+
+
 __host__ __device__ constexpr int OeStages(int C) { return C >= 8 ? 4 : 8; }  // operand ring depth
 __host__ __device__ constexpr int OePrefetchOps(int C) { return OeStages(C) / 2; }
 __host__ __device__ constexpr int OeGroup(int C) { return kThreads / C; }  // patterns per j-slab

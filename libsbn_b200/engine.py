@@ -129,7 +129,10 @@ class StagedBatch:
 class Engine:
     """B200 likelihood engine for one alignment and one phylo-model specification."""
 
-    def __init__(self, specification, patterns, weights, device=0):
+    def __init__(self, specification, patterns, weights, device=0, devices=None, shard_axis="trees"):
+        """device: one CUDA ordinal; or devices=[...]: a device group inside the library
+        (sbnb_engine_create_multi: one host thread + stream per GPU), sharded by
+        "trees" or by "patterns" (SURVEY.md 8e)."""
         lib = _capi.load()
         patterns = np.ascontiguousarray(patterns, dtype=np.uint8)
         weights = np.ascontiguousarray(weights, dtype=np.float64)
@@ -138,13 +141,22 @@ class Engine:
         self.specification = specification
         self.taxon_count, self.pattern_count = patterns.shape
         handle = ctypes.c_void_p()
-        _capi.check(lib.sbnb_engine_create(
-            specification.substitution.encode(), specification.site.encode(),
-            specification.clock.encode(), self.taxon_count, self.pattern_count,
-            patterns.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _capi.as_double_ptr(weights),
-            device, ctypes.byref(handle)))
+        common = (specification.substitution.encode(), specification.site.encode(),
+                  specification.clock.encode(), self.taxon_count, self.pattern_count,
+                  patterns.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _capi.as_double_ptr(weights))
+        if devices is None:
+            _capi.check(lib.sbnb_engine_create(*common, device, ctypes.byref(handle)))
+        else:
+            if shard_axis not in ("trees", "patterns"):
+                raise RuntimeError("shard_axis must be 'trees' or 'patterns'.")
+            ordinals = np.ascontiguousarray(devices, dtype=np.int32)
+            axis = _capi.SHARD_TREES if shard_axis == "trees" else _capi.SHARD_PATTERNS
+            _capi.check(lib.sbnb_engine_create_multi(*common, _capi.as_int32_ptr(ordinals), len(ordinals), axis,
+                                                     ctypes.byref(handle)))
+            device = int(ordinals[0])
         self._handle = handle
         self.device = device
+        self.device_count = lib.sbnb_engine_device_count(handle)
         self.param_count = lib.sbnb_engine_param_count(handle)
         self.category_count = lib.sbnb_engine_category_count(handle)
 

@@ -216,13 +216,18 @@ class PatternShardedEngine:
             import torch
             pointers = [ctypes.c_void_p() for _ in range(3)]
             _capi.check(lib.sbnb_batch_device_results(staged._handle, *[ctypes.byref(p) for p in pointers]))
+            # The three result arrays are one contiguous fp64 array on the device:
+            # [evaluations] log-likelihoods, [T x (2n-1)] edge derivatives and, with more than
+            # one rate category, [T x (2n-1)] rate derivatives -- one collective.
             T, N = staged.tree_count, staged.node_count
-            counts = [lib.sbnb_batch_evaluation_count(staged._handle) if arrays_wanted > 1 else T, T * N, T * N]
+            if arrays_wanted > 1:
+                count = lib.sbnb_batch_evaluation_count(staged._handle) + (2 if pointers[2].value else 1) * T * N
+            else:
+                count = T
             stream = torch.cuda.ExternalStream(self.engine.stream, device=self.engine.device)
             with torch.cuda.stream(stream):  # NCCL is ordered after the walk kernels on the engine's stream
-                for pointer, count in list(zip(pointers, counts))[:arrays_wanted]:
-                    view = torch.as_tensor(_DeviceArrayView(pointer.value, count), device=f"cuda:{self.engine.device}")
-                    _dist().all_reduce(view, op=_dist().ReduceOp.SUM)
+                view = torch.as_tensor(_DeviceArrayView(pointers[0].value, count), device=f"cuda:{self.engine.device}")
+                _dist().all_reduce(view, op=_dist().ReduceOp.SUM)
             stream.synchronize()
             return staged.fetch(gradients=arrays_wanted > 1)
         result = staged.fetch(gradients=arrays_wanted > 1)

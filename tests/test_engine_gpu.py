@@ -323,3 +323,21 @@ def test_error_behaviour():
     assert rel(good, fx["log_likelihoods"]) < LOGL_RTOL
     empty = engine.log_likelihoods(batch_of(fx).slice(0, 0), fx["params"][:0], False)
     assert empty.shape == (0,)
+
+
+def test_unrooted_gradient_of_a_bifurcating_tree_slides_the_root(oracle):
+    """The reference's unrooted Gradient applies Tree::SlideRootPosition after
+    Detrifurcate (fat_beagle.cpp:470-472, tree.cpp:72-78): a no-op for a detrifurcated
+    tree, but for bifurcating input the root's second child gets length 0 and its
+    first child the sum -- the engine must do the same (and the oracle does)."""
+    fx = load_fixture("flua_jc69_weibull4_strict")
+    spec = sbn.PhyloModelSpecification("JC69", "weibull+4", "none")
+    engine = sbn.Engine(spec, fx["patterns"], fx["weights"])
+    batch = sbn.TreeBatch(fx["parent_ids"], fx["branch_lengths"])
+    params = fx["params"][:, :1]
+    got = engine.gradients(batch, params, True)
+    want = oracle.gradients("JC69", "weibull+4", fx["patterns"], fx["weights"], fx["parent_ids"],
+                            fx["branch_lengths"], params, rescaling=True)
+    assert rel([g.log_likelihood for g in got], want["log_likelihood"]) < LOGL_RTOL
+    assert grad_rel(stack(got, "branch_lengths"), want["branch"]) < GRAD_RTOL
+    assert grad_rel(stack(got, "site_model").T, want["site_model"][None, :]) < GRAD_RTOL
