@@ -201,13 +201,19 @@ class PatternShardedEngine:
     """Engine restricted to this rank's range of site patterns; batch calls walk
     ALL trees over the local patterns and sum-all-reduce the raw results."""
 
-    def __init__(self, specification, patterns, weights, device=0):
+    def __init__(self, specification, patterns, weights, device=0, presharded=False):
+        """presharded: `patterns` / `weights` are already this rank's columns only (an
+        alignment too large to build on every rank); otherwise every rank passes the
+        whole alignment and keeps its range of it."""
         self.rank, self.world, self.backend = _world()
         self.specification = specification
         self.engine = Engine(specification, patterns, weights, device)
-        self.begin, self.end = pattern_range(self.rank, self.world, self.engine.pattern_count)
-        if self.world > 1:
-            self.engine.set_pattern_range(self.begin, self.end)
+        if presharded:
+            self.begin, self.end = 0, self.engine.pattern_count
+        else:
+            self.begin, self.end = pattern_range(self.rank, self.world, self.engine.pattern_count)
+            if self.world > 1:
+                self.engine.set_pattern_range(self.begin, self.end)
 
     def _reduce(self, staged, arrays_wanted):
         """All-reduce of the raw result arrays of a finished run, then fetch."""

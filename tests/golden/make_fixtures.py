@@ -208,6 +208,29 @@ def unrooted_cases_newick_ds1():
 
 
 @case
+def unrooted_cases_newick_ds1_config2():
+    # BASELINE configs[1] exactly: DS1 x DS1.100_topologies.nwk with
+    # branch lengths ~ Exp(mean 0.1) (numpy default_rng(1), tree-major), GTR + weibull4 with
+    # the rooted_sbn_instance.hpp:336-337 rates / frequencies and shape 0.5: the
+    # reference's log_likelihoods() and full phylo_gradients() for all 100 trees.
+    def exponential_lengths(inst):
+        rng = np.random.default_rng(1)
+        for tree in inst.tree_collection.trees:
+            lengths = np.array(tree.branch_lengths, copy=False)
+            lengths[:-1] = np.maximum(rng.exponential(0.1, size=lengths.size - 1), 1e-6)
+
+    def gtr_weibull(block_map):
+        block_map["GTR rates"][:] = [0.05, 0.1, 0.15, 0.20, 0.25, 0.25]
+        block_map["frequencies"][:] = [0.1, 0.2, 0.3, 0.4]
+        block_map["Weibull shape"][:] = 0.5
+
+    unrooted_case("ds1_100_topologies_gtr_weibull4", newick=f"{DATA}/DS1.100_topologies.nwk",
+                  fasta=f"{DATA}/DS1.fasta", spec=("GTR", "weibull+4", "none"), set_params=gtr_weibull,
+                  set_lengths=exponential_lengths)
+
+
+
+@case
 def unrooted_cases_nexus_reordered():
     # test/test_libsbn.py:95-118: JC69 == GTR(equal) on DS1 tree 0, all branches 0.1.
     def only_first_tree_01(inst):

@@ -12,7 +12,7 @@ import pytest
 
 from conftest import load_fixture
 
-UNROOTED = ["hello_jc69", "ds1_jc69", "ds1_jc69_weibull4", "ds1_gtr_weibull4",
+UNROOTED = ["hello_jc69", "ds1_jc69", "ds1_jc69_weibull4", "ds1_gtr_weibull4", "ds1_100_topologies_gtr_weibull4",
             "ds1_100_topologies_jc69", "ds1_tree0_gtr_equal"]
 ROOTED = ["flua_jc69_strict", "flua_jc69_varied_rates", "flua_gtr_strict", "flua_jc69_weibull4_strict"]
 
