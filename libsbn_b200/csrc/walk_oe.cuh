@@ -396,7 +396,6 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
   const int ops_total = GRAD ? 2 * internal_count : internal_count;
   constexpr int kStages = OeStages(C);
   constexpr int kPrefetch = OePrefetchOps(C);
-  constexpr int kGroup = OeGroup(C);
   constexpr int kTilePatterns = OeTilePatterns(C, K);
   constexpr int kTipBytes = OeTipBytes(C, K);
   constexpr int kStage = OeStageBytes(C, K);
@@ -533,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
       double w[K];
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        const int64_t pattern = pat0 + j * kGroup + pidx;
+        const int64_t pattern = pat0 + pidx * K + j;  // a thread's K patterns are adjacent
         w[j] = (pattern < p.pattern_end) ? p.weights[pattern] : 0.0;
       }
 
@@ -567,8 +566,15 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
         }
         __syncwarp();
         const double* const operand = reinterpret_cast<const double*>(stage) + kOeHeaderDoubles;
-        const uint8_t* const tips_a = stage + kOperandBytes + pidx;
-        const uint8_t* const tips_b = tips_a + kTipBytes;
+        // the tip states of this thread's K adjacent patterns: one load per tip child
+        const unsigned char* const tips_at = stage + kOperandBytes + pidx * K;
+        auto tip_states = [&](const unsigned char* at) -> uint32_t {
+          if (K == 4) return *reinterpret_cast<const uint32_t*>(at);
+          if (K == 2) return *reinterpret_cast<const uint16_t*>(at);
+          return *at;
+        };
+        // doubles from the start of a category's tip table to the row of pattern j's state
+        auto tip_row = [](uint32_t packed, int j) -> int { return ((packed >> (8 * j)) & 0xff) * 4; };
         // The host orders the children of every op so that an internal child whose
         // partial is (post-order) or stays (pre-order) in cur is child a, and a child
         // that goes through the stack is child b: a leaf => b leaf.
@@ -605,9 +611,9 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
           const double* const part_b = operand + (a_leaf ? kLeafPart : kInnerPart);
           // ---- child a
           if (a_leaf) {
+            const uint32_t states_a = tip_states(tips_at);
 #pragma unroll
-            for (int j = 0; j < K; j++)
-              Load4(operand + cat * kTipTableDoubles + tips_a[j * kGroup] * 4, ya[j]);
+            for (int j = 0; j < K; j++) Load4(operand + cat * kTipTableDoubles + tip_row(states_a, j), ya[j]);
             if (RESCALE) {
 #pragma unroll
               for (int j = 0; j < K; j++) cur_exp[j] = 0;
@@ -618,9 +624,9 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
           }
           // ---- child b
           if (b_leaf) {
+            const uint32_t states_b = tip_states(tips_at + kTipBytes);
 #pragma unroll
-            for (int j = 0; j < K; j++)
-              Load4(part_b + cat * kTipTableDoubles + tips_b[j * kGroup] * 4, yb[j]);
+            for (int j = 0; j < K; j++) Load4(part_b + cat * kTipTableDoubles + tip_row(states_b, j), yb[j]);
           } else {
             const int s2 = (record.y >> 16) & 0xff;
             double x[K][4];
@@ -680,6 +686,8 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
           const int next_children = ((flags & kNextALeaf) ? 0 : 1) + ((flags & kNextBLeaf) ? 0 : 1);
           // read-back order of two internal children: the post-order op's child order
           const bool swapped = flags & kArenaSwapped;
+          const uint32_t states_a = a_leaf ? tip_states(tips_at) : 0;
+          const uint32_t states_b = b_leaf ? tip_states(tips_at + kTipBytes) : 0;
           double g_own = 0.0, g_a = 0.0, g_b = 0.0;
 #pragma unroll
           for (int batch = 0; batch < kBatches; batch++) {
@@ -707,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
             if (a_leaf) {
 #pragma unroll
               for (int j = 0; j < KP; j++)
-                Load4(table_a + cat * kTipTableDoubles + tips_a[(j0 + j) * kGroup] * 4, ya[j]);
+                Load4(table_a + cat * kTipTableDoubles + tip_row(states_a, j0 + j), ya[j]);
             } else {
               const double2* const slot_a = slot + ((swapped && !b_leaf) ? KP * 64 : 0);
 #pragma unroll
@@ -719,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
             if (b_leaf) {
 #pragma unroll
               for (int j = 0; j < KP; j++)
-                Load4(table_b + cat * kTipTableDoubles + tips_b[(j0 + j) * kGroup] * 4, yb[j]);
+                Load4(table_b + cat * kTipTableDoubles + tip_row(states_b, j0 + j), yb[j]);
             } else {
               const double2* const slot_b = slot + (swapped ? 0 : KP * 64);
 #pragma unroll
@@ -771,7 +779,7 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
 #pragma unroll
               for (int j = 0; j < KP; j++) {
                 double d[4];
-                Load4(table_a + (C + cat) * kTipTableDoubles + tips_a[(j0 + j) * kGroup] * 4, d);
+                Load4(table_a + (C + cat) * kTipTableDoubles + tip_row(states_a, j0 + j), d);
                 g_a = fma(scale[j], Dot4(top[j], d), g_a);
               }
             }
@@ -804,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
 #pragma unroll
               for (int j = 0; j < KP; j++) {
                 double d[4];
-                Load4(table_b + (C + cat) * kTipTableDoubles + tips_b[(j0 + j) * kGroup] * 4, d);
+                Load4(table_b + (C + cat) * kTipTableDoubles + tip_row(states_b, j0 + j), d);
                 g_b = fma(scale[j], Dot4(yb[j], d), g_b);
               }
             } else {
