@@ -14,6 +14,7 @@
 #include <string>
 
 #include "sbn_b200.h"
+#include "scoped_gil_release.hpp"
 
 namespace {
 
@@ -203,8 +204,13 @@ std::vector<double> Engine::LogLikelihoods(const UnrootedTreeCollection &tree_co
   trees.AddTopologiesAndBranchLengths(tree_collection);
   const auto params = ContiguousParams(phylo_model_params, tree_collection.TreeCount());
   std::vector<double> results(tree_collection.TreeCount());
-  Check(sbnb_log_likelihoods_unrooted(device_engine_, &trees.batch, params.data(), rescaling,
-                                      results.data()));
+  int status = SBNB_OK;
+  {
+    ScopedGilRelease let_python_threads_run;
+    status = sbnb_log_likelihoods_unrooted(device_engine_, &trees.batch, params.data(), rescaling,
+                                      results.data());
+  }
+  Check(status);
   return results;
 }
 
@@ -216,8 +222,13 @@ std::vector<double> Engine::LogLikelihoods(const RootedTreeCollection &tree_coll
   trees.AddTimeTreeExtras(tree_collection);
   const auto params = ContiguousParams(phylo_model_params, tree_collection.TreeCount());
   std::vector<double> results(tree_collection.TreeCount());
-  Check(sbnb_log_likelihoods_rooted(device_engine_, &trees.batch, params.data(), rescaling,
-                                    results.data()));
+  int status = SBNB_OK;
+  {
+    ScopedGilRelease let_python_threads_run;
+    status = sbnb_log_likelihoods_rooted(device_engine_, &trees.batch, params.data(), rescaling,
+                                    results.data());
+  }
+  Check(status);
   return results;
 }
 
@@ -228,8 +239,13 @@ std::vector<double> Engine::UnrootedLogLikelihoods(
   trees.AddTopologiesAndBranchLengths(tree_collection);
   const auto params = ContiguousParams(phylo_model_params, tree_collection.TreeCount());
   std::vector<double> results(tree_collection.TreeCount());
-  Check(sbnb_unrooted_log_likelihoods_of_rooted(device_engine_, &trees.batch, params.data(),
-                                                rescaling, results.data()));
+  int status = SBNB_OK;
+  {
+    ScopedGilRelease let_python_threads_run;
+    status = sbnb_unrooted_log_likelihoods_of_rooted(device_engine_, &trees.batch, params.data(),
+                                                rescaling, results.data());
+  }
+  Check(status);
   return results;
 }
 
@@ -255,8 +271,13 @@ std::vector<PhyloGradient> Engine::Gradients(const UnrootedTreeCollection &tree_
   // Detrifurcate adds a node (unrooted_tree.cpp:27-37).
   blocks.out.branch_lengths =
       blocks.Add("branch_lengths", 2 * site_pattern_.SequenceCount() - 1);
-  Check(sbnb_gradients_unrooted(device_engine_, &trees.batch, params.data(), rescaling,
-                                &blocks.out));
+  int status = SBNB_OK;
+  {
+    ScopedGilRelease let_python_threads_run;
+    status = sbnb_gradients_unrooted(device_engine_, &trees.batch, params.data(), rescaling,
+                                &blocks.out);
+  }
+  Check(status);
   return blocks.Collect();
 }
 
@@ -283,7 +304,12 @@ std::vector<PhyloGradient> Engine::Gradients(const RootedTreeCollection &tree_co
       blocks.Add("ratios_root_height", site_pattern_.SequenceCount() - 1);
   blocks.out.clock_model =
       blocks.Add("clock_model", static_cast<size_t>(std::max(trees.batch.rate_count, 0)));
-  Check(sbnb_gradients_rooted(device_engine_, &trees.batch, params.data(), rescaling,
-                              &blocks.out));
+  int status = SBNB_OK;
+  {
+    ScopedGilRelease let_python_threads_run;
+    status = sbnb_gradients_rooted(device_engine_, &trees.batch, params.data(), rescaling,
+                              &blocks.out);
+  }
+  Check(status);
   return blocks.Collect();
 }

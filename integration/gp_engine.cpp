@@ -13,6 +13,7 @@
 #include <limits>
 
 #include "sbn_b200_gp.h"
+#include "scoped_gil_release.hpp"
 #include "sugar.hpp"
 
 namespace {
@@ -140,8 +141,13 @@ GPEngine::GPEngine(SitePattern site_pattern, size_t plv_count, size_t gpcsp_coun
 GPEngine::~GPEngine() { sbnb_gp_destroy(device_engine_); }
 
 void GPEngine::Run(const std::vector<int32_t> &program) {
-  Check(sbnb_gp_process_operations(device_engine_, program.data(),
-                                   static_cast<int64_t>(program.size())));
+  int status = SBNB_OK;
+  {
+    ScopedGilRelease let_python_threads_run;
+    status = sbnb_gp_process_operations(device_engine_, program.data(),
+                                        static_cast<int64_t>(program.size()));
+  }
+  Check(status);
 }
 
 void GPEngine::operator()(const GPOperations::ZeroPLV &op) { Run(EncodeOne(op)); }

@@ -275,6 +275,7 @@ LaunchPlan Dispatch(sbnb_engine* e, const OeParams& p, bool grad, bool rescale, 
     case 2:
       return DispatchModesOe<2, 2, 4>(e, p, grad, rescale, launch, chunks_override);
     case 4:
+      // (measured: 4 patterns per thread at 12 warps/SM beat 2 at 16 warps/SM by 8 %)
       return DispatchModesOe<4, 4, 4>(e, p, grad, rescale, launch, chunks_override);
     case 8:
       return DispatchModesOe<8, 2, 2>(e, p, grad, rescale, launch, chunks_override);

@@ -31,6 +31,7 @@ summary["stall_share_pct"] = {k: round(100 * v / total, 2) for k, v in sorted(st
 dram = (f("dram__bytes_read.sum") * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[d["dram__bytes_read.sum"][0]] +
         f("dram__bytes_write.sum") * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[d["dram__bytes_write.sum"][0]])
 summary["trees_in_capture"] = trees
+summary["git_sha"] = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
 summary["dram_bytes_per_tree"] = dram / trees
 summary["dram_bytes_per_launch_at_bench_size"] = dram / trees * 1024
 summary["algorithmic_bytes_per_tree"] = (10 * 100 - 14) * 32 * 4 * 100000

@@ -64,6 +64,9 @@ def test_reference_doctest_suite_passes_on_the_device():
     """reference src/doctest.cpp: every test case, including the pybeagle / physher /
     phylotorch goldens of {un,}rooted_sbn_instance.hpp, through sbn_b200.h."""
     _compare_with_reference_build("doctest", ("likelihood", "gradients", "time trees"), 42)
+    with open(_artefact("doctest"), "rb") as handle:
+        # SitePattern::Compress is integration/site_pattern.cpp (device) in this build
+        assert b"IntVectorHasher" not in handle.read(), "the reference SitePattern::Compress is still linked in"
 
 
 @pytest.mark.gpu
@@ -143,3 +146,52 @@ def test_reference_doctest_fails_loudly_without_a_device():
         _artefact("doctest"), "-tc=UnrootedSBNInstance: likelihood and gradient with Weibull")
     assert code != 0 and failed == 1
     assert "no CPU fallback" in text
+
+
+_GIL_CASE = textwrap.dedent("""
+    import sys, threading, time
+    sys.path.insert(0, sys.argv[1])
+    import libsbn
+    inst = libsbn.unrooted_instance("ds1")
+    inst.read_newick_file("data/DS1.100_topologies.nwk")
+    inst.read_fasta_file("data/DS1.fasta")
+    inst.prepare_for_phylo_likelihood(libsbn.PhyloModelSpecification("GTR", "weibull+4", "none"), 1, [], True)
+    block_map = inst.get_phylo_model_param_block_map()
+    block_map["GTR rates"][:] = [0.05, 0.1, 0.15, 0.20, 0.25, 0.25]
+    block_map["frequencies"][:] = [0.1, 0.2, 0.3, 0.4]
+    block_map["Weibull shape"][:] = 0.5
+    inst.phylo_gradients()  # warm up
+    ticks, inside, stop = [0, 0], [False], [False]
+    def spin():
+        while not stop[0]:
+            ticks[1 if inside[0] else 0] += 1
+            time.sleep(0)
+    thread = threading.Thread(target=spin)
+    thread.start()
+    t0 = time.perf_counter()
+    inside[0] = True
+    for _ in range(200):
+        inst.phylo_gradients()
+    inside[0] = False
+    elapsed = time.perf_counter() - t0
+    stop[0] = True
+    thread.join()
+    print("TICKS_INSIDE", ticks[1], "ELAPSED", elapsed)
+""")
+
+
+@pytest.mark.gpu
+def test_device_calls_release_the_gil():
+    """a Python thread keeps running while the reference's (unchanged)
+    python module is inside phylo_gradients() on the device -- the replacement Engine
+    releases the GIL around every libsbn_b200 call (integration/scoped_gil_release.hpp)."""
+    _artefact("doctest")
+    done = subprocess.run([sys.executable, "-c", _GIL_CASE, BUILD], cwd=REF_RUN_DIR, capture_output=True,
+                          text=True, timeout=600)
+    assert done.returncode == 0, done.stderr[-2000:]
+    found = re.search(r"TICKS_INSIDE (\d+) ELAPSED ([\d.]+)", done.stdout)
+    assert found, done.stdout[-2000:]
+    ticks, elapsed = int(found.group(1)), float(found.group(2))
+    # with the GIL held across the calls the other thread only gets the gaps between
+    # them (a few switch intervals); released, it spins the whole time
+    assert ticks > 2000 * elapsed, (ticks, elapsed)
