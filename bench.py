@@ -581,14 +581,23 @@ def run_ours(args):
     if not args.quick:
         # ---- the reference's full GTR phylo_gradients through the public call ------------
         full = lambda: engine.gradients(shard, shard_params, rescaling=True, substitution_gradient=True)
-        full()
-        full_steps = max(1, min(args.steps, 2))
-        full_ms = timed(full, full_steps)
         line["e2e_full_phylo_gradients"] = {
-            "value": args.trees * full_steps / (full_ms * 1e-3), "unit": "trees/s",
-            "ms_per_tree_per_gpu": full_ms / full_steps / max(local_trees, 1),
-            "what": "logL + branch + site-model + substitution-model gradients; the substitution block by the "
-                    "reference's 16 central-difference log-likelihood sweeps per tree (fat_beagle.cpp:400-465)"}
+            "unit": "trees/s",
+            "what": "logL + branch + site-model + substitution-model gradients through the public call; the "
+                    "substitution block either exactly, inside the gradient sweep (analytic: W = sum of w/lik "
+                    "(V^T T)(V^-1 L)^T o Phi over edges, categories and patterns, contracted with V^-1 dQ/dtheta V "
+                    "on the host), or by the reference's 16 central-difference log-likelihood sweeps per tree "
+                    "(finite_differences; fat_beagle.cpp:400-465)"}
+        for mode, key in (("analytic", "analytic"), ("fd", "finite_differences")):
+            engine.set_substitution_gradient(mode)
+            full()
+            full_steps = max(1, min(args.steps, 2))
+            full_ms = timed(full, full_steps)
+            line["e2e_full_phylo_gradients"][key] = {
+                "value": args.trees * full_steps / (full_ms * 1e-3),
+                "ms_per_tree_per_gpu": full_ms / full_steps / max(local_trees, 1)}
+        engine.set_substitution_gradient("analytic")
+        line["e2e_full_phylo_gradients"]["value"] = line["e2e_full_phylo_gradients"]["analytic"]["value"]
 
         # ---- weak scaling beside the strong headline (N > 1) ---------------------------
         if world > 1:

@@ -91,6 +91,21 @@ int sbnb_engine_create_multi(const char* substitution, const char* site, const c
                              int32_t taxon_count, int64_t pattern_count, const uint8_t* tip_states,
                              const double* pattern_weights, const int32_t* devices,
                              int32_t device_count, int32_t shard_axis, sbnb_engine** out);
+/*
+ * How the "substitution_model" block of a gradient call (GTR: 8 entries, HKY: 4) is
+ * computed.  The reference takes central differences of 16 full log-likelihood
+ * evaluations per tree (fat_beagle.cpp:400-465, delta 1e-6 in stick-breaking
+ * coordinates); SBNB_SUBSTITUTION_ANALYTIC (the default; or SBNB_SUBSTITUTION_GRADIENT=fd
+ * in the environment for the other) computes the exact derivative inside the gradient
+ * sweep: with P = V exp(Lambda tau) V^-1, dP/dtheta = V [(V^-1 dQ/dtheta V) o Phi(tau)] V^-1,
+ * so the sweep only accumulates W_kl = sum of w/lik (V^T T)_k (V^-1 L)_l Phi_kl over edges,
+ * categories and patterns (16 numbers per tree) and the host contracts them with
+ * V^-1 dQ/dtheta V.  It differs from the reference's values by their O(delta^2)
+ * truncation and O(eps/delta) rounding error.  SBNB_SUBSTITUTION_FINITE_DIFFERENCES
+ * reproduces the reference's arithmetic.
+ */
+enum { SBNB_SUBSTITUTION_ANALYTIC = 0, SBNB_SUBSTITUTION_FINITE_DIFFERENCES = 1 };
+int sbnb_engine_set_substitution_gradient(sbnb_engine* engine, int32_t mode);
 /* Number of devices behind an engine (1 unless created with sbnb_engine_create_multi). */
 int32_t sbnb_engine_device_count(const sbnb_engine* engine);
 
@@ -258,6 +273,14 @@ int sbnb_debug_model_tables(const char* substitution, const char* site, const ch
                             double* inverse_eigenvectors, double* eigenvalues, double* frequencies,
                             double* q, double* category_rates, double* category_weights,
                             double* category_rate_derivatives);
+
+/* The host part of the analytic substitution-parameter gradient for one parameter
+ * row: per gradient coordinate theta (GTR: 5 rate + 3 frequency stick-breaking
+ * coordinates; HKY: kappa + 3), B_theta = V^-1 (dQ/dtheta) V as b[theta][16] (row-major)
+ * and d pi / d theta as dfreqs[theta][4]; *count = number of coordinates. */
+int sbnb_debug_substitution_derivatives(const char* substitution, const char* site, const char* clock,
+                                        const double* param_row, double* b, double* dfreqs,
+                                        int32_t* count);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,7 @@ SIGNATURES = {
                                             _P(_c.c_uint8), _P(_c.c_double), _P(_c.c_int32), _c.c_int32,
                                             _c.c_int32, _P(_c.c_void_p)]),
     "sbnb_engine_device_count": (_c.c_int32, [_c.c_void_p]),
+    "sbnb_engine_set_substitution_gradient": (_c.c_int, [_c.c_void_p, _c.c_int32]),
     "sbnb_engine_destroy": (None, [_c.c_void_p]),
     "sbnb_engine_param_count": (_c.c_int32, [_c.c_void_p]),
     "sbnb_engine_param_block": (_c.c_int, [_c.c_void_p, _c.c_char_p, _P(_c.c_int32), _P(_c.c_int32)]),
@@ -94,6 +95,8 @@ SIGNATURES = {
     "sbnb_debug_tree_program": (_c.c_int, [_P(_c.c_int32), _c.c_int32, _c.c_int32, _P(_c.c_int32),
                                            _P(_c.c_int32), _P(_c.c_int32)]),
     "sbnb_debug_model_tables": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p] + [_P(_c.c_double)] * 9),
+    "sbnb_debug_substitution_derivatives": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _P(_c.c_double),
+                                                       _P(_c.c_double), _P(_c.c_double), _P(_c.c_int32)]),
 }
 
 # Every symbol include/sbn_b200_gp.h declares.
@@ -134,6 +137,8 @@ STAGE_ROOTED = 1
 STAGE_SUBSTITUTION_FD = 2
 SHARD_TREES = 0
 SHARD_PATTERNS = 1
+SUBSTITUTION_ANALYTIC = 0
+SUBSTITUTION_FINITE_DIFFERENCES = 1
 
 _lib = None
 

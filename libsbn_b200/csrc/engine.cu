@@ -101,6 +101,9 @@ struct sbnb_engine {
   // for one child engine per device; see the "device groups" section below.
   std::vector<sbnb_engine*> children;
   int shard_axis = 0;
+  // How "substitution_model" gradients are computed: analytically in the gradient sweep
+  // (default), or by the reference's 16 central-difference log-likelihood sweeps.
+  int substitution_mode = SBNB_SUBSTITUTION_ANALYTIC;
 
   ~sbnb_engine();
 };
@@ -112,6 +115,7 @@ struct sbnb_batch {
   bool rooted = false;
   bool slide_root = false;
   int fd_coords = 0;  // stick-breaking coordinates perturbed (0 if no FD staged)
+  bool with_subst = false;  // staged for the analytic substitution gradient (Phi in the pre-order blocks)
   int vtree_count = 0;
   int slots = 1;
   int last_mode = -1;
@@ -124,6 +128,7 @@ struct sbnb_batch {
   // re-evaluates the same trees with new branch lengths, vip/burrito.py:84-117).
   std::vector<int32_t> cached_parent_ids;
   int cached_input_nodes = 0, cached_padded_categories = 0;
+  bool cached_with_subst = false;
   // device side: one packed input buffer
   //   [lengths | models | vtree_program | vtree_model | vtree_lengths]   every call
   //   [ops | edge_offsets]                                              per topology set
@@ -133,8 +138,8 @@ struct sbnb_batch {
   int64_t post_doubles = 0, full_doubles = 0;  // operand block of a logL-only / a gradient evaluation
   int64_t operand_stride = 0;                  // of the base trees' blocks in `operands` (last run)
   DeviceArray<double> operands;                // operand blocks of the base trees
-  DeviceArray<double> logl_partial, grad_partial, rgrad_partial;
-  DeviceArray<double> results;  // [logl (vtree_count) | grad (T x N) | rgrad (T x N)]
+  DeviceArray<double> logl_partial, grad_partial, rgrad_partial, subst_partial;
+  DeviceArray<double> results;  // [logl (vtree_count) | grad (T x N) | rgrad (T x N) | subst sums (T x 20)]
   // tiling of the last run
   int chunks = 1;
 
@@ -145,6 +150,7 @@ struct sbnb_batch {
   double* ResultLogl() const { return results.get(); }
   double* ResultGrad() const { return results.get() + vtree_count; }
   double* ResultRateGrad() const { return ResultGrad() + static_cast<size_t>(tree_count) * node_count; }
+  double* ResultSubst() const { return ResultRateGrad() + static_cast<size_t>(tree_count) * node_count; }
 };
 
 sbnb_engine::~sbnb_engine() {
@@ -185,11 +191,12 @@ struct LaunchPlan {
 };
 
 // Plans (and launches) TreeWalkOeKernel, whose tiles are kThreads / C * K patterns.
-template <int C, int K, bool GRAD, bool RESCALE>
+template <int C, int K, bool GRAD, bool RESCALE, bool SUBST = false>
 LaunchPlan PlanAndLaunchOe(sbnb_engine* e, OeParams p, bool launch, int chunks_override) {
-  auto kernel = TreeWalkOeKernel<C, K, GRAD, RESCALE>;
+  auto kernel = TreeWalkOeKernel<C, K, GRAD, RESCALE, SUBST>;
   // (SBNB_EXTRA_SMEM: development aid -- pads the request to lower the resident CTA count)
-  const size_t smem = OeSmemBytes(C, K, GRAD) + static_cast<size_t>(std::max(0, EnvInt("SBNB_EXTRA_SMEM", 0)));
+  const size_t smem =
+      OeSmemBytes(C, K, GRAD, SUBST) + static_cast<size_t>(std::max(0, EnvInt("SBNB_EXTRA_SMEM", 0)));
   static thread_local int cached_device = -1, cached_per_sm = 0;
   static thread_local size_t cached_smem = 0;
   if (cached_device != e->device || cached_smem != smem) {
@@ -249,16 +256,19 @@ LaunchPlan PlanAndLaunchOe(sbnb_engine* e, OeParams p, bool launch, int chunks_o
   return plan;
 }
 
-template <int C, int K, bool GRAD>
+template <int C, int K, bool GRAD, bool SUBST = false>
 LaunchPlan DispatchRescale(sbnb_engine* e, const OeParams& p, bool rescale, bool launch, int chunks_override) {
-  return rescale ? PlanAndLaunchOe<C, K, GRAD, true>(e, p, launch, chunks_override)
-                 : PlanAndLaunchOe<C, K, GRAD, false>(e, p, launch, chunks_override);
+  return rescale ? PlanAndLaunchOe<C, K, GRAD, true, SUBST>(e, p, launch, chunks_override)
+                 : PlanAndLaunchOe<C, K, GRAD, false, SUBST>(e, p, launch, chunks_override);
 }
 
-// K_GRAD / K_LOGL patterns per thread for the gradient / logL-only walk.
+// K_GRAD / K_LOGL patterns per thread for the gradient / logL-only walk; a gradient walk
+// with p.subst_partial set also accumulates the analytic substitution-gradient sums.
 template <int C, int K_GRAD, int K_LOGL>
 LaunchPlan DispatchModesOe(sbnb_engine* e, const OeParams& p, bool grad, bool rescale, bool launch,
                            int chunks_override) {
+  if (grad && p.subst_partial != nullptr)
+    return DispatchRescale<C, K_GRAD, true, true>(e, p, rescale, launch, chunks_override);
   return grad ? DispatchRescale<C, K_GRAD, true>(e, p, rescale, launch, chunks_override)
               : DispatchRescale<C, K_LOGL, false>(e, p, rescale, launch, chunks_override);
 }
@@ -425,8 +435,9 @@ void EffectiveBranchLengths(const TreeProgram& program, const sbnb_tree_batch* t
 // whose partial is in cur (post-order) or stays in cur (pre-order), child b the one
 // that goes through the stack -- so a tip child a implies a tip child b, and the
 // kernel has no "which child uses cur" cases.
-void PackProgram(const TreeProgram& program, int n, int C, OeOp* ops, int2* edge_offsets, int64_t* post_doubles,
-                 int64_t* full_doubles) {
+void PackProgram(const TreeProgram& program, int n, int C, bool with_subst, OeOp* ops, int2* edge_offsets,
+                 int64_t* post_doubles, int64_t* full_doubles) {
+  const int phi_part = with_subst ? kOePhiDoubles * C : 0;  // behind every edge's part of a pre-order block
   Require(program.post_slots < 255 && program.pre_slots < 255 && 2 * n - 1 < (1 << 24), "Tree too large.");
   auto slot_byte = [](int32_t slot) { return slot < 0 ? 0xff : (slot & 0xff); };
   const int inner_part = kPStride * C, leaf_part = kTipTableDoubles * C;
@@ -482,14 +493,14 @@ void PackProgram(const TreeProgram& program, int n, int C, OeOp* ops, int2* edge
     OeOp& out = ops[n - 1 + o];
     int64_t part = kOeHeaderDoubles;
     if (!root) edge_offsets[op.node].y = static_cast<int32_t>(at + part);
-    part += inner_part;  // (the root's op gets an identity there)
+    part += inner_part + phi_part;  // (the root's op gets an identity there)
     if (a_leaf) {
       edge_offsets[a].y = static_cast<int32_t>(at + part);
-      part += 2 * leaf_part;
+      part += 2 * leaf_part + phi_part;
     }
     if (b_leaf) {
       edge_offsets[b].y = static_cast<int32_t>(at + part);
-      part += 2 * leaf_part;
+      part += 2 * leaf_part + phi_part;
     }
     out.operand_unit = static_cast<int32_t>(at / 2);
     out.operand_units = static_cast<int32_t>(part / 2);
@@ -519,7 +530,7 @@ void WaitForStaging(sbnb_engine* e) {
 }
 
 BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params, bool rooted,
-               bool with_fd, bool slide_root) {
+               bool with_fd, bool slide_root, bool with_subst = false) {
   CheckTrees(e, trees, rooted);
   const ModelSpec& spec = e->spec;
   Require(spec.param_count == 0 || params != nullptr || trees->tree_count == 0,
@@ -538,6 +549,7 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   batch->categories = e->categories;
   const int fd_evals = with_fd ? 2 * spec.SubstitutionGradientSize() : 0;
   batch->fd_coords = fd_evals / 2;
+  batch->with_subst = with_subst;
   batch->vtree_count = T * (1 + fd_evals);
   if (T == 0) return batch;
 
@@ -565,7 +577,8 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   // Is this the topology set whose programs are already on the device?
   const size_t id_count = static_cast<size_t>(T) * (trees->node_count - 1);
   const bool cached = same_shape && batch->cached_input_nodes == trees->node_count &&
-                      batch->cached_padded_categories == C && batch->cached_parent_ids.size() == id_count &&
+                      batch->cached_padded_categories == C && batch->cached_with_subst == with_subst &&
+                      batch->cached_parent_ids.size() == id_count &&
                       batch->input.capacity() >= total_bytes &&
                       std::memcmp(batch->cached_parent_ids.data(), trees->parent_ids, id_count * sizeof(int32_t)) == 0;
 
@@ -589,7 +602,7 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
     ParallelOverTrees(T, [&](int t) {
       TreeProgram program = BuildTreeProgram(
           trees->parent_ids + static_cast<size_t>(t) * (trees->node_count - 1), trees->node_count, n);
-      PackProgram(program, n, C, ops + static_cast<size_t>(t) * 2 * (n - 1),
+      PackProgram(program, n, C, with_subst, ops + static_cast<size_t>(t) * 2 * (n - 1),
                   edge_offsets + static_cast<size_t>(t) * (2 * n - 2), &post_doubles[t], &full_doubles[t]);
       tree_slots[t] = std::max(program.post_slots, program.pre_slots);
       program.post.clear();
@@ -605,6 +618,7 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
     batch->cached_parent_ids.assign(trees->parent_ids, trees->parent_ids + id_count);
     batch->cached_input_nodes = trees->node_count;
     batch->cached_padded_categories = C;
+    batch->cached_with_subst = with_subst;
   }
   for (int t = 0; t < T; t++)
     EffectiveBranchLengths(batch->programs[t], trees, t, rooted, batch->slide_root, N,
@@ -649,7 +663,7 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   SBNB_CUDA(cudaEventRecord(e->staging_free, s));
   e->staging_in_flight = true;
   e->h2d_bytes += copy_bytes;
-  batch->results.Reserve(batch->vtree_count + 2 * static_cast<size_t>(T) * N);
+  batch->results.Reserve(batch->vtree_count + 2 * static_cast<size_t>(T) * N + static_cast<size_t>(T) * kOeSubstSums);
   return batch;
 }
 
@@ -684,7 +698,7 @@ OeParams BaseParams(sbnb_engine* e, sbnb_batch* b) {
 // Transition matrices of virtual trees [begin, begin + count), written into the
 // operand blocks of the ops that read them, and the block headers.
 void LaunchMatrices(sbnb_engine* e, sbnb_batch* b, double* operands, int64_t stride, int begin, int count,
-                    bool with_pre) {
+                    bool with_pre, bool with_subst = false) {
   const int n = e->taxon_count, C = e->padded_categories;
   OeMatrixParams m{};
   m.models = b->At<ModelTables>(b->models_at);
@@ -701,6 +715,7 @@ void LaunchMatrices(sbnb_engine* e, sbnb_batch* b, double* operands, int64_t str
   m.taxon_count = n;
   m.categories = C;
   m.with_pre = with_pre ? 1 : 0;
+  m.with_subst = (with_pre && with_subst) ? 1 : 0;
   m.prefetch = OePrefetchOps(C);
   const int64_t jobs = static_cast<int64_t>(count) * (2 * n - 2) * C +
                        static_cast<int64_t>(count) * (with_pre ? 2 * (n - 1) : n - 1);
@@ -731,12 +746,15 @@ void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
   OeParams p = BaseParams(e, b);
   p.vtree_begin = 0;
   p.vtree_count = T;
+  // (which walk is planned: the one with the substitution-gradient sums has its own occupancy)
+  if (grad && b->with_subst) p.subst_partial = reinterpret_cast<double*>(1);
   LaunchPlan plan = Dispatch(e, p, grad, rescaling, /*launch=*/false, 0);
   LaunchPlan fd_plan{};
   if (fd_vtrees > 0) {
     OeParams q = p;
     q.vtree_begin = T;
     q.vtree_count = slice;
+    q.subst_partial = nullptr;
     fd_plan = Dispatch(e, q, false, rescaling, false, 0);
   }
   // Partial-sum rows: [vtree][chunk][warp]; all launches share one chunk count so
@@ -746,19 +764,22 @@ void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
   b->chunks = chunks;
   const size_t rows = static_cast<size_t>(vtrees) * chunks * kWarps;
   b->logl_partial.Reserve(rows);
+  const bool subst = grad && b->with_subst;
   if (grad) {
     const size_t grad_rows = static_cast<size_t>(T) * chunks * kWarps * N;
     b->grad_partial.Reserve(grad_rows);
     if (C > 1) b->rgrad_partial.Reserve(grad_rows);
+    if (subst) b->subst_partial.Reserve(static_cast<size_t>(T) * chunks * kWarps * kOeSubstSums);
   }
   p.logl_partial = b->logl_partial.get();
   p.grad_partial = b->grad_partial.get();
   p.rgrad_partial = b->rgrad_partial.get();
+  p.subst_partial = subst ? b->subst_partial.get() : nullptr;
 
   // Base trees: matrices, then the logL or gradient sweep.
   b->operand_stride = grad ? b->full_doubles : b->post_doubles;
   b->operands.Reserve(static_cast<size_t>(T) * b->operand_stride);
-  LaunchMatrices(e, b, b->operands.get(), b->operand_stride, 0, T, grad);
+  LaunchMatrices(e, b, b->operands.get(), b->operand_stride, 0, T, grad, b->with_subst);
   p.operands = b->operands.get();
   p.operand_origin = 0;
   p.operand_stride = b->operand_stride;
@@ -786,17 +807,19 @@ void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
 
   // Fixed-order reduction of the per-(chunk, warp) partial sums, all arrays at once.
   {
-    const int64_t total = vtrees + (grad ? 2 * static_cast<int64_t>(T) * N : 0);
+    const int64_t total = vtrees + (grad ? 2 * static_cast<int64_t>(T) * N : 0) +
+                          (subst ? static_cast<int64_t>(T) * kOeSubstSums : 0);
     const int block = 128;
     ReduceAllKernel<<<static_cast<int>((total + block - 1) / block), block, 0, s>>>(
         b->logl_partial.get(), b->grad_partial.get(), (grad && C > 1) ? b->rgrad_partial.get() : nullptr,
-        b->results.get(), 0, vtrees, b->vtree_count, grad ? T : 0, N, chunks * kWarps);
+        subst ? b->subst_partial.get() : nullptr, b->results.get(), 0, vtrees, b->vtree_count, grad ? T : 0, N,
+        chunks * kWarps);
     SBNB_CUDA(cudaGetLastError());
     e->launch_count++;
   }
 }
 
-void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rgrad) {
+void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rgrad, double* subst = nullptr) {
   SBNB_CUDA(cudaSetDevice(e->device));
   Require(b->last_mode >= 0, "sbnb_batch_fetch called before sbnb_batch_run.");
   const bool was_grad = (b->last_mode == SBNB_MODE_BRANCH_GRADIENT);
@@ -807,7 +830,10 @@ void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rg
   if (b->tree_count > 0) {
     // One copy of what is asked for into page-locked memory, then out to the caller's arrays.
     const bool rates = rgrad && e->padded_categories > 1;
-    const size_t count = (grad || rates) ? b->vtree_count + (rates ? 2 : 1) * grad_count : vtrees;
+    const size_t subst_count = static_cast<size_t>(b->tree_count) * kOeSubstSums;
+    if (subst) Require(was_grad && b->with_subst, "No substitution-gradient sums: the batch was not staged for them.");
+    const size_t count = subst ? b->vtree_count + 2 * grad_count + subst_count
+                               : ((grad || rates) ? b->vtree_count + (rates ? 2 : 1) * grad_count : vtrees);
     e->landing.Reset(count * sizeof(double));
     double* landed = e->landing.Take<double>(count);
     SBNB_CUDA(cudaMemcpyAsync(landed, b->results.get(), count * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -822,6 +848,9 @@ void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rg
         std::fill(rgrad, rgrad + grad_count, 0.0);
       }
     }
+    if (subst)
+      std::copy(landed + b->vtree_count + 2 * grad_count, landed + b->vtree_count + 2 * grad_count + subst_count,
+                subst);
   } else {
     SBNB_CUDA(cudaStreamSynchronize(s));
   }
@@ -885,6 +914,9 @@ std::unique_ptr<sbnb_engine> CreateEngine(const char* substitution, const char* 
     engine->host_tips = tips;
     engine->host_weights = std::make_shared<std::vector<double>>(pattern_weights, pattern_weights + pattern_count);
   }
+  if (const char* mode = std::getenv("SBNB_SUBSTITUTION_GRADIENT"))
+    engine->substitution_mode = std::string(mode) == "fd" ? SBNB_SUBSTITUTION_FINITE_DIFFERENCES
+                                                           : SBNB_SUBSTITUTION_ANALYTIC;
   UploadPatternRange(engine.get(), 0, pattern_count);
   return engine;
 }
@@ -913,7 +945,8 @@ void LogLikelihoods(sbnb_engine* e, const sbnb_tree_batch* trees, const double* 
 // and each runs this once.
 void FinishGradients(const ModelSpec& spec, int n, const sbnb_tree_batch* trees, bool rooted, int fd_coords,
                      const double* logl, const double* grad, const double* rgrad,
-                     const sbnb_gradient_out* out, const std::vector<TreeProgram>* programs = nullptr) {
+                     const sbnb_gradient_out* out, const std::vector<TreeProgram>* programs = nullptr,
+                     const double* params = nullptr, const double* subst_sums = nullptr) {
   Require(trees != nullptr, "NULL tree batch.");
   Require(out != nullptr, "NULL gradient output.");
   const int T = trees->tree_count, N = 2 * n - 1;
@@ -936,6 +969,21 @@ void FinishGradients(const ModelSpec& spec, int n, const sbnb_tree_batch* trees,
       for (int k = 0; k < fd_coords; k++)
         out->substitution_model[static_cast<size_t>(t) * fd_coords + k] =
             (fd[2 * k] - fd[2 * k + 1]) / (2. * kFiniteDifferenceDelta);
+    }
+    if (out->substitution_model && subst_sums != nullptr) {
+      // Analytic: d logL / d theta = < W, B_theta > + d pi / d theta . R (model.hpp).
+      const double* row = params + static_cast<size_t>(t) * spec.param_count;
+      ModelTables tables;
+      BuildModelTables(spec, row, &tables);
+      SubstitutionDerivatives derivatives;
+      BuildSubstitutionDerivatives(spec, row, tables, &derivatives);
+      const double* sums = subst_sums + static_cast<size_t>(t) * kOeSubstSums;
+      for (int k = 0; k < derivatives.count; k++) {
+        double value = 0.0;
+        for (int e = 0; e < 16; e++) value += sums[e] * derivatives.b[k][e];
+        for (int j = 0; j < 4; j++) value += sums[16 + j] * derivatives.dfreqs[k][j];
+        out->substitution_model[static_cast<size_t>(t) * derivatives.count + k] = value;
+      }
     }
     if (out->site_model && categories > 1) {
       EffectiveBranchLengths(tree, trees, t, rooted, /*slide_root=*/true, N, lengths.data());
@@ -964,16 +1012,17 @@ void Gradients(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
                bool rooted, const sbnb_gradient_out* out) {
   Require(out != nullptr, "NULL gradient output.");
   Require(trees != nullptr, "NULL tree batch.");
-  const int fd_coords = e->spec.SubstitutionGradientSize();
-  auto batch = Stage(e, trees, params, rooted, fd_coords > 0 && out->substitution_model != nullptr,
-                     /*slide_root=*/true);
+  const int coords = e->spec.SubstitutionGradientSize();
+  const bool wanted = coords > 0 && out->substitution_model != nullptr;
+  const bool analytic = wanted && e->substitution_mode == SBNB_SUBSTITUTION_ANALYTIC;
+  auto batch = Stage(e, trees, params, rooted, wanted && !analytic, /*slide_root=*/true, analytic);
   Run(e, batch.get(), SBNB_MODE_BRANCH_GRADIENT, rescaling);
   const int T = trees->tree_count, N = 2 * e->taxon_count - 1;
   std::vector<double> logl(batch->vtree_count), grad(static_cast<size_t>(T) * N),
-      rgrad(static_cast<size_t>(T) * N);
-  Fetch(e, batch.get(), logl.data(), grad.data(), rgrad.data());
+      rgrad(static_cast<size_t>(T) * N), subst(analytic ? static_cast<size_t>(T) * kOeSubstSums : 0);
+  Fetch(e, batch.get(), logl.data(), grad.data(), rgrad.data(), analytic && T > 0 ? subst.data() : nullptr);
   FinishGradients(e->spec, e->taxon_count, trees, rooted, batch->fd_coords, logl.data(), grad.data(),
-                  rgrad.data(), out, &batch->programs);
+                  rgrad.data(), out, &batch->programs, params, analytic && T > 0 ? subst.data() : nullptr);
 }
 
 
@@ -1031,13 +1080,14 @@ sbnb_tree_batch SliceTrees(const sbnb_tree_batch* trees, int n, int begin, int e
 // Pattern axis: stage + run on every child, sum the raw results onto child 0.
 // Returns child 0's batch (results complete once its stream has been synchronised).
 std::vector<BatchPtr> RunOverPatternShards(sbnb_engine* group, const sbnb_tree_batch* trees, const double* params,
-                                           bool rooted, bool with_fd, bool slide_root, int mode, bool rescaling) {
+                                           bool rooted, bool with_fd, bool slide_root, int mode, bool rescaling,
+                                           bool with_subst = false) {
   const int G = static_cast<int>(group->children.size());
   std::vector<BatchPtr> batches;
   for (int g = 0; g < G; g++) batches.emplace_back(nullptr, BatchRecycler{group->children[g]});
   std::vector<cudaEvent_t> done(G, nullptr);
   ParallelOverChildren(group, [&](int g, sbnb_engine* child) {
-    batches[g] = Stage(child, trees, params, rooted, with_fd, slide_root);
+    batches[g] = Stage(child, trees, params, rooted, with_fd, slide_root, with_subst);
     Run(child, batches[g].get(), mode, rescaling);
     if (g > 0) {
       SBNB_CUDA(cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming));
@@ -1049,9 +1099,10 @@ std::vector<BatchPtr> RunOverPatternShards(sbnb_engine* group, const sbnb_tree_b
   if (trees->tree_count > 0 && G > 1) {
     SBNB_CUDA(cudaSetDevice(first->device));
     const bool grad = (mode == SBNB_MODE_BRANCH_GRADIENT);
-    const int64_t count =
-        grad ? b0->vtree_count + (first->padded_categories > 1 ? 2 : 1) * static_cast<int64_t>(b0->tree_count) * b0->node_count
-             : b0->tree_count;
+    const int64_t edges = static_cast<int64_t>(b0->tree_count) * b0->node_count;
+    const int64_t count = !grad ? b0->tree_count
+                                : (with_subst ? b0->vtree_count + 2 * edges + b0->tree_count * kOeSubstSums
+                                              : b0->vtree_count + (first->padded_categories > 1 ? 2 : 1) * edges);
     PeerPointers peers{};
     peers.part[0] = b0->results.get();
     for (int g = 1; g < G; g++) {
@@ -1124,6 +1175,8 @@ void GroupGradients(sbnb_engine* group, const sbnb_tree_batch* trees, const doub
   const int G = static_cast<int>(group->children.size()), T = trees->tree_count, n = group->taxon_count;
   const int N = 2 * n - 1, K = group->spec.param_count;
   const int fd_coords = group->spec.SubstitutionGradientSize();
+  const bool wanted = fd_coords > 0 && out->substitution_model != nullptr;
+  const bool analytic = wanted && group->substitution_mode == SBNB_SUBSTITUTION_ANALYTIC;
   if (group->shard_axis == SBNB_SHARD_TREES) {
     ParallelOverChildren(group, [&](int g, sbnb_engine* child) {
       const int begin = static_cast<int>(static_cast<int64_t>(T) * g / G);
@@ -1143,14 +1196,14 @@ void GroupGradients(sbnb_engine* group, const sbnb_tree_batch* trees, const doub
     });
     return;
   }
-  auto batches = RunOverPatternShards(group, trees, params, rooted,
-                                      fd_coords > 0 && out->substitution_model != nullptr, true,
-                                      SBNB_MODE_BRANCH_GRADIENT, rescaling);
+  auto batches = RunOverPatternShards(group, trees, params, rooted, wanted && !analytic, true,
+                                      SBNB_MODE_BRANCH_GRADIENT, rescaling, analytic);
   sbnb_batch* b0 = batches[0].get();
-  std::vector<double> logl(b0->vtree_count), grad(static_cast<size_t>(T) * N), rgrad(static_cast<size_t>(T) * N);
-  Fetch(group->children[0], b0, logl.data(), grad.data(), rgrad.data());
+  std::vector<double> logl(b0->vtree_count), grad(static_cast<size_t>(T) * N), rgrad(static_cast<size_t>(T) * N),
+      subst(analytic ? static_cast<size_t>(T) * kOeSubstSums : 0);
+  Fetch(group->children[0], b0, logl.data(), grad.data(), rgrad.data(), analytic && T > 0 ? subst.data() : nullptr);
   FinishGradients(group->spec, n, trees, rooted, b0->fd_coords, logl.data(), grad.data(), rgrad.data(), out,
-                  &b0->programs);
+                  &b0->programs, params, analytic && T > 0 ? subst.data() : nullptr);
 }
 
 bool IsGroup(const sbnb_engine* e) { return !e->children.empty(); }
@@ -1213,7 +1266,18 @@ int sbnb_engine_create_multi(const char* substitution, const char* site, const c
     group->pattern_count = first->pattern_count;
     group->categories = first->categories;
     group->padded_categories = first->padded_categories;
+    group->substitution_mode = first->substitution_mode;
     *out = group.release();
+  });
+}
+
+int sbnb_engine_set_substitution_gradient(sbnb_engine* engine, int32_t mode) {
+  return Guard([&] {
+    Require(engine != nullptr, "NULL engine.");
+    Require(mode == SBNB_SUBSTITUTION_ANALYTIC || mode == SBNB_SUBSTITUTION_FINITE_DIFFERENCES,
+            "Unknown substitution-gradient mode.");
+    engine->substitution_mode = mode;
+    for (sbnb_engine* child : engine->children) child->substitution_mode = mode;
   });
 }
 
@@ -1478,6 +1542,24 @@ int sbnb_debug_model_tables(const char* substitution, const char* site, const ch
     if (category_rates) std::copy(tables.rates, tables.rates + C, category_rates);
     if (category_weights) std::copy(tables.weights, tables.weights + C, category_weights);
     if (category_rate_derivatives) std::copy(tables.drates, tables.drates + C, category_rate_derivatives);
+  });
+}
+
+int sbnb_debug_substitution_derivatives(const char* substitution, const char* site, const char* clock,
+                                        const double* param_row, double* b, double* dfreqs, int32_t* count) {
+  return Guard([&] {
+    Require(substitution && site && clock && b && dfreqs && count, "NULL argument.");
+    const ModelSpec spec = ModelSpec::Parse(substitution, site, clock);
+    Require(spec.param_count == 0 || param_row != nullptr, "NULL parameter row.");
+    ModelTables tables;
+    BuildModelTables(spec, param_row, &tables);
+    SubstitutionDerivatives derivatives;
+    BuildSubstitutionDerivatives(spec, param_row, tables, &derivatives);
+    *count = derivatives.count;
+    for (int t = 0; t < derivatives.count; t++) {
+      std::copy(derivatives.b[t], derivatives.b[t] + 16, b + 16 * t);
+      std::copy(derivatives.dfreqs[t], derivatives.dfreqs[t] + 4, dfreqs + 4 * t);
+    }
   });
 }
 

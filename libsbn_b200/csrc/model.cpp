@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <sstream>
+#include <vector>
 
 #include "common.hpp"
 
@@ -394,6 +395,124 @@ void StickBreaking(const double* y, int simplex_size, double* x) {
     stick -= x[k];
   }
   x[simplex_size - 1] = stick;
+}
+
+void StickBreakingJacobian(const double* y, int simplex_size, double* jacobian) {
+  const int coords = simplex_size - 1;
+  double stick = 1.0;
+  std::vector<double> dstick(coords, 0.0);  // d stick / d y_j
+  for (int k = 0; k < coords; k++) {
+    const double z = 1.0 / (1.0 + std::exp(-(y[k] - std::log(double(simplex_size - k - 1)))));
+    for (int j = 0; j < coords; j++) {
+      // x_k = stick z_k
+      const double dx = dstick[j] * z + (j == k ? stick * z * (1.0 - z) : 0.0);
+      jacobian[k * coords + j] = dx;
+      dstick[j] -= dx;
+    }
+    stick -= stick * z;
+  }
+  for (int j = 0; j < coords; j++) jacobian[coords * coords + j] = dstick[j];  // x_last = the rest of the stick
+}
+
+void BuildSubstitutionDerivatives(const ModelSpec& spec, const double* row, const ModelTables& tables,
+                                  SubstitutionDerivatives* out) {
+  out->count = 0;
+  if (spec.substitution == SubstitutionKind::kJC69) return;
+  const bool gtr = spec.substitution == SubstitutionKind::kGTR;
+  const double* freqs = row + spec.Block("frequencies").first;
+  double rates[6];
+  if (gtr) {
+    std::copy(row + spec.Block("GTR rates").first, row + spec.Block("GTR rates").first + 6, rates);
+  } else {
+    const double kappa = row[spec.Block("kappa").first];
+    const double hky[6] = {1.0, kappa, 1.0, 1.0, kappa, 1.0};
+    std::copy(hky, hky + 6, rates);
+  }
+  // exchangeability of the pair (i, j), order AC AG AT CG CT GT
+  int pair_a[6], pair_b[6], index = 0;
+  double r[4][4] = {};
+  for (int i = 0; i < 4; i++)
+    for (int j = i + 1; j < 4; j++) {
+      pair_a[index] = i, pair_b[index] = j;
+      r[i][j] = r[j][i] = rates[index++];
+    }
+  double mu = 0.0;  // the expected rate the unnormalised matrix is divided by
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++)
+      if (i != j) mu += freqs[i] * r[i][j] * freqs[j];
+  // d Q / d (one exchangeability), d Q / d (one frequency): Q = Qu / mu.
+  auto finish = [&](double (&dqu)[16], double dmu, double* dq) {
+    for (int e = 0; e < 16; e++) dq[e] = (dqu[e] - tables.q[e] * dmu) / mu;
+  };
+  double dq_rate[6][16], dq_freq[4][16];
+  for (int m = 0; m < 6; m++) {
+    const int a = pair_a[m], b = pair_b[m];
+    double dqu[16] = {};
+    dqu[a * 4 + b] = freqs[b];
+    dqu[b * 4 + a] = freqs[a];
+    dqu[a * 4 + a] = -freqs[b];
+    dqu[b * 4 + b] = -freqs[a];
+    finish(dqu, 2.0 * freqs[a] * freqs[b], dq_rate[m]);
+  }
+  for (int k = 0; k < 4; k++) {
+    double dqu[16] = {};
+    double dmu = 0.0;
+    for (int i = 0; i < 4; i++) {
+      if (i == k) continue;
+      dqu[i * 4 + k] = r[i][k];
+      dqu[i * 4 + i] = -r[i][k];
+      dmu += 2.0 * r[k][i] * freqs[i];
+    }
+    finish(dqu, dmu, dq_freq[k]);
+  }
+  // chain rule through the parametrisation
+  double dq[8][16] = {};
+  auto add = [](double* to, const double* from, double factor) {
+    for (int e = 0; e < 16; e++) to[e] += factor * from[e];
+  };
+  int count = 0;
+  if (gtr) {
+    double y[5], jacobian[6 * 5];
+    StickBreakingInverse(rates, 6, y);
+    StickBreakingJacobian(y, 6, jacobian);
+    for (int k = 0; k < 5; k++, count++) {
+      for (int m = 0; m < 6; m++) add(dq[count], dq_rate[m], jacobian[m * 5 + k]);
+      std::fill(out->dfreqs[count], out->dfreqs[count] + 4, 0.0);
+    }
+  } else {
+    add(dq[count], dq_rate[1], 1.0);  // kappa multiplies the two transitions A<->G, C<->T
+    add(dq[count], dq_rate[4], 1.0);
+    std::fill(out->dfreqs[count], out->dfreqs[count] + 4, 0.0);
+    count++;
+  }
+  {
+    double y[3], jacobian[4 * 3];
+    StickBreakingInverse(freqs, 4, y);
+    StickBreakingJacobian(y, 4, jacobian);
+    for (int k = 0; k < 3; k++, count++) {
+      for (int m = 0; m < 4; m++) {
+        add(dq[count], dq_freq[m], jacobian[m * 3 + k]);
+        out->dfreqs[count][m] = jacobian[m * 3 + k];
+      }
+    }
+  }
+  // B = V^-1 dQ V
+  for (int t = 0; t < count; t++) {
+    double left[16];
+    for (int k = 0; k < 4; k++)
+      for (int j = 0; j < 4; j++) {
+        double sum = 0.0;
+        for (int i = 0; i < 4; i++) sum += tables.ivec[k * 4 + i] * dq[t][i * 4 + j];
+        left[k * 4 + j] = sum;
+      }
+    for (int k = 0; k < 4; k++)
+      for (int l = 0; l < 4; l++) {
+        double sum = 0.0;
+        for (int j = 0; j < 4; j++) sum += left[k * 4 + j] * tables.evec[j * 4 + l];
+        out->b[t][k * 4 + l] = sum;
+      }
+  }
+  out->count = count;
 }
 
 void StickBreakingInverse(const double* x, int simplex_size, double* y) {

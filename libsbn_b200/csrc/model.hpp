@@ -60,6 +60,25 @@ void BuildSite(const ModelSpec& spec, const double* params, ModelTables* out);
 // Whole row -> tables.
 void BuildModelTables(const ModelSpec& spec, const double* row, ModelTables* out);
 
+// Analytic substitution-parameter gradient, host part.  With
+// P = exp(Q tau) = V exp(Lambda tau) V^-1,
+//     d P / d theta = V [ (V^-1 dQ/dtheta V) o Phi(tau) ] V^-1,
+//     Phi_kl = (e^{lambda_k tau} - e^{lambda_l tau}) / (lambda_k - lambda_l)   (tau e^{lambda_k tau} when equal),
+// so  d logL / d theta = < W, B_theta > + d pi / d theta . R  with  B_theta = V^-1 dQ/dtheta V  and the
+// device sums  W_kl = sum over edges, categories, patterns of  w/lik (V^T T)_k (V^-1 L)_l Phi_kl,
+// R_j = sum of w/lik p_c L_root,j.  theta runs over the reference's gradient coordinates
+// (fat_beagle.cpp:440-465): GTR -> 5 stick-breaking coordinates of the rates, then 3 of the
+// frequencies; HKY -> kappa, then 3 of the frequencies.
+struct SubstitutionDerivatives {
+  int count = 0;
+  double b[8][16];      // B_theta, row-major
+  double dfreqs[8][4];  // d pi / d theta
+};
+void BuildSubstitutionDerivatives(const ModelSpec& spec, const double* row, const ModelTables& tables,
+                                  SubstitutionDerivatives* out);
+// d x / d y of the stick-breaking transform: jacobian[m * (simplex_size - 1) + k] = d x_m / d y_k.
+void StickBreakingJacobian(const double* y, int simplex_size, double* jacobian);
+
 // stick_breaking_transform.cpp:20-43: simplex <-> unconstrained coordinates.
 void StickBreaking(const double* y, int simplex_size, double* x);
 void StickBreakingInverse(const double* x, int simplex_size, double* y);

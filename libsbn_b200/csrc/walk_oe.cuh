@@ -74,8 +74,11 @@ enum : int32_t { kArenaSwapped = 16, kNextALeaf = 64, kNextBLeaf = 128 };
 //   pre-order op:   own P (18 C; an identity at the root), then per TIP child 40 C:
 //                   per c P_c^T + ones, per c (Q P_c)^T + zeros
 constexpr int kOeHeaderDoubles = 8;
-__host__ __device__ constexpr int OeMaxOperandDoubles(int C) {
-  return kOeHeaderDoubles + (kPStride + 4 * kTipTableDoubles) * C;
+// (with the analytic substitution gradient every edge's part of a pre-order block is
+//  followed by Phi_c, 16 doubles per category: see OeMatrixParams::with_subst)
+constexpr int kOePhiDoubles = 16;
+__host__ __device__ constexpr int OeMaxOperandDoubles(int C, bool subst = false) {
+  return kOeHeaderDoubles + (kPStride + 4 * kTipTableDoubles + (subst ? 3 * kOePhiDoubles : 0)) * C;
 }
 
 struct OeParams {
@@ -100,6 +103,7 @@ struct OeParams {
   double* logl_partial;    // [vtree][chunk][warp]
   double* grad_partial;    // [vtree][chunk][warp][2n-1]               (gradient mode)
   double* rgrad_partial;   // same, with d rate_c / d shape as the scalers (C > 1)
+  double* subst_partial;   // [vtree][chunk][warp][kOeSubstSums]        (analytic substitution gradient)
 };
 
 // ---------------------------------------------------------------------------
@@ -125,6 +129,9 @@ struct OeMatrixParams {
   int32_t taxon_count;
   int32_t categories;   // padded
   int32_t with_pre;     // the run has a pre-order half
+  int32_t with_subst;   // ... whose blocks also carry Phi for the analytic substitution gradient:
+                        //     Phi_kl = (e^{l_k tau} - e^{l_l tau}) / (l_k - l_l), tau e^{l_k tau} on the
+                        //     diagonal (tau = r_c t), after the edge's matrix / tip tables
   int32_t prefetch;     // OePrefetchOps(C)
 };
 
@@ -157,6 +164,8 @@ __global__ void TransitionMatrixOeKernel(const OeMatrixParams p) {
       double* identity = reinterpret_cast<double*>(header) + kOeHeaderDoubles;
       for (int c = 0; c < C; c++)
         for (int k = 0; k < kPStride; k++) identity[c * kPStride + k] = (k < 16 && k % 5 == 0) ? 1.0 : 0.0;
+      if (p.with_subst)  // (no edge: no d P / d theta term)
+        for (int k = 0; k < kOePhiDoubles * C; k++) identity[kPStride * C + k] = 0.0;
     }
     return;
   }
@@ -202,6 +211,23 @@ __global__ void TransitionMatrixOeKernel(const OeMatrixParams p) {
     write_matrix(block + offsets.x);
   }
   if (!p.with_pre || offsets.y < 0) return;
+  if (p.with_subst) {
+    double2* out = reinterpret_cast<double2*>(block + offsets.y + (tip ? 2 * kTipTableDoubles : kPStride) * C +
+                                              kOePhiDoubles * c);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      double row[4];
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        // e^{l_l tau} tau (e^x - 1) / x,  x = (l_k - l_l) tau
+        const double x = (model.eval[k] - model.eval[l]) * t;
+        const double ratio = fabs(x) < 1e-8 ? 1.0 + 0.5 * x : expm1(x) / x;
+        row[l] = ex[l] * t * ratio;
+      }
+      out[2 * k] = make_double2(row[0], row[1]);
+      out[2 * k + 1] = make_double2(row[2], row[3]);
+    }
+  }
   if (!tip) {
     write_matrix(block + offsets.y);
     return;
@@ -223,15 +249,29 @@ __global__ void TransitionMatrixOeKernel(const OeMatrixParams p) {
   out[9] = make_double2(0.0, 0.0);
 }
 
+constexpr int kOeSubstSums = 20;  // W (16) and R (4) of the analytic substitution gradient
+
 // One launch for all three result arrays: out = [logl (logl_count) | grad (rows x width) |
 // rgrad (rows x width)], each entry the fixed-order sum of its `parts` per-(chunk, warp)
 // partial rows (bitwise deterministic run to run).
 __global__ void ReduceAllKernel(const double* __restrict__ logl_partial, const double* __restrict__ grad_partial,
-                                const double* __restrict__ rgrad_partial, double* __restrict__ out,
-                                int32_t logl_begin, int32_t logl_count, int32_t logl_total, int32_t grad_rows,
-                                int32_t width, int32_t parts) {
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+                                const double* __restrict__ rgrad_partial, const double* __restrict__ subst_partial,
+                                double* __restrict__ out, int32_t logl_begin, int32_t logl_count,
+                                int32_t logl_total, int32_t grad_rows, int32_t width, int32_t parts) {
+  int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t grad_count = static_cast<int64_t>(grad_rows) * width;
+  if (subst_partial != nullptr && idx >= logl_count + 2 * grad_count) {
+    // the substitution-gradient sums: [tree][kOeSubstSums] after the three arrays
+    idx -= logl_count + 2 * grad_count;
+    if (idx >= static_cast<int64_t>(grad_rows) * kOeSubstSums) return;
+    const int64_t row = idx / kOeSubstSums;
+    const int e = static_cast<int>(idx % kOeSubstSums);
+    const double* src = subst_partial + row * parts * kOeSubstSums + e;
+    double sum = 0.0;
+    for (int part = 0; part < parts; part++) sum += src[static_cast<int64_t>(part) * kOeSubstSums];
+    out[logl_total + 2 * grad_count + idx] = sum;
+    return;
+  }
   if (idx < logl_count) {
     const int64_t v = logl_begin + idx;
     const double* src = logl_partial + v * parts;
@@ -279,19 +319,22 @@ __host__ __device__ constexpr int OePrefetchOps(int C) { return OeStages(C) / 2;
 __host__ __device__ constexpr int OeGroup(int C) { return kThreads / C; }  // patterns per j-slab
 __host__ __device__ constexpr int OeTilePatterns(int C, int K) { return OeGroup(C) * K; }
 __host__ __device__ constexpr int OeTipBytes(int C, int K) { return (OeTilePatterns(C, K) + 15) / 16 * 16; }
-__host__ __device__ constexpr int OeStageBytes(int C, int K) {
-  return OeMaxOperandDoubles(C) * 8 + 2 * OeTipBytes(C, K);
+__host__ __device__ constexpr int OeStageBytes(int C, int K, bool subst = false) {
+  return OeMaxOperandDoubles(C, subst) * 8 + 2 * OeTipBytes(C, K);
 }
 // The pre-order op works through its K patterns in sub-batches of at most 2.
 __host__ __device__ constexpr int OePreBatch(int K) { return K > 2 ? 2 : K; }
 // Read-back slots of one pre-order op: [warp][batch][child][j][half][lane] double2.
 __host__ __device__ constexpr int OeReadbackBytes(int K) { return 2 * K * 2 * kThreads * 16; }
-__host__ __device__ constexpr size_t OeSmemBytes(int C, int K, bool grad) {
-  return static_cast<size_t>(OeStages(C)) * OeStageBytes(C, K) + 2 * OeStages(C) * 8 +
-         kModelSmemDoubles * 8 + 16 + 2 * kWarps * 8 + (grad ? OeReadbackBytes(K) : 0);
+// model constants of the analytic substitution gradient: V, V^-1, and V^-1 e_s per tip state
+constexpr int kOeSubstSmemDoubles = 16 + 16 + 20;
+__host__ __device__ constexpr size_t OeSmemBytes(int C, int K, bool grad, bool subst = false) {
+  return static_cast<size_t>(OeStages(C)) * OeStageBytes(C, K, subst) + 2 * OeStages(C) * 8 +
+         (kModelSmemDoubles + kOeSubstSmemDoubles) * 8 + 16 + 2 * kWarps * 8 + (grad ? OeReadbackBytes(K) : 0);
 }
 // Resident CTAs per SM the register allocation is held to.
-__host__ __device__ constexpr int OeMinBlocks(int K, bool grad) {
+__host__ __device__ constexpr int OeMinBlocks(int K, bool grad, bool subst = false) {
+  if (subst) return 2;  // 16 + 4 more accumulators per thread
   return grad ? 3 : (K <= 2 ? 4 : 3);
 }
 
@@ -377,8 +420,9 @@ __device__ __forceinline__ void NormalizeOe(double (&v)[K][4], int (&exps)[K]) {
   }
 }
 
-template <int C, int K, bool GRAD, bool RESCALE>
-__global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKernel(const OeParams p) {
+template <int C, int K, bool GRAD, bool RESCALE, bool SUBST = false>
+__global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD, SUBST)) TreeWalkOeKernel(const OeParams p) {
+  static_assert(GRAD || !SUBST, "the substitution gradient rides on the pre-order pass");
   static_assert((C & (C - 1)) == 0 && C >= 1 && C <= 16, "lanes per pattern must be a power of two");
   static_assert(OeTilePatterns(C, K) % 16 == 0, "tiles must start on 16-byte boundaries of the tip rows");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -398,8 +442,9 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
   constexpr int kPrefetch = OePrefetchOps(C);
   constexpr int kTilePatterns = OeTilePatterns(C, K);
   constexpr int kTipBytes = OeTipBytes(C, K);
-  constexpr int kStage = OeStageBytes(C, K);
-  constexpr int kOperandBytes = OeMaxOperandDoubles(C) * 8;
+  constexpr int kStage = OeStageBytes(C, K, SUBST);
+  constexpr int kOperandBytes = OeMaxOperandDoubles(C, SUBST) * 8;
+  constexpr int kPhiPart = SUBST ? kOePhiDoubles * C : 0;  // doubles of Phi behind an edge's part
   constexpr int kRow = 2 * kThreads;  // double2 per pattern slab: [half][tid]
   constexpr int KP = OePreBatch(K);   // patterns per pre-order sub-batch ...
   constexpr int kBatches = K / KP;    // ... and sub-batches per op, each with its own barrier
@@ -416,9 +461,12 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
   double* const rate_weight_smem = cat_weight_smem + kMaxCategories;
   double* const drate_weight_smem = rate_weight_smem + kMaxCategories;
   double* const freqs_smem = drate_weight_smem + kMaxCategories;
+  double* const evec_smem = freqs_smem + 4;  // V, V^-1 and V^-1 e_s (s = A C G T, gap): analytic substitution gradient
+  double* const ivec_smem = evec_smem + 16;
+  double* const tip_z_smem = ivec_smem + 16;
   // Sequence number of the next op whose operands have not been requested yet.
-  uint32_t* const ticket = reinterpret_cast<uint32_t*>(freqs_smem + 4);
-  uint64_t* const readback_bars = reinterpret_cast<uint64_t*>(freqs_smem + 6);
+  uint32_t* const ticket = reinterpret_cast<uint32_t*>(tip_z_smem + 20);
+  uint64_t* const readback_bars = reinterpret_cast<uint64_t*>(tip_z_smem + 22);
   uint64_t* const readback_full = readback_bars + warp * 2;
   // Read-back slots, [warp][batch][child][j][half][lane] double2, filled per warp by
   // bulk copies that complete on the warp's own barriers.
@@ -463,6 +511,17 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
       rate_weight_smem[tid] = model.rates[tid];    // r_c  (p_c rides in the pre-order partials)
       drate_weight_smem[tid] = model.drates[tid];  // dr_c/dshape
       if (tid < 4) freqs_smem[tid] = model.freqs[tid];
+      if (SUBST) {
+        evec_smem[tid] = model.evec[tid];
+        ivec_smem[tid] = model.ivec[tid];
+      }
+    }
+    if (SUBST && tid >= 32 && tid < 52) {
+      // V^-1 L for a tip: column s of V^-1 for a resolved state, the row sums for a gap
+      const int state = (tid - 32) / 4, k = (tid - 32) % 4;
+      tip_z_smem[tid - 32] = state < 4 ? model.ivec[k * 4 + state]
+                                       : model.ivec[k * 4] + model.ivec[k * 4 + 1] + model.ivec[k * 4 + 2] +
+                                             model.ivec[k * 4 + 3];
     }
     if (GRAD) {
       // This warp owns its rows of edge-derivative sums for the whole item: clear them
@@ -527,6 +586,32 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
     int g = 0;
 
     double logl_acc = 0.0;
+    // analytic substitution gradient: W_kl = sum of w/lik (V^T T)_k (V^-1 L)_l Phi_kl over edges and
+    // patterns, R_l = sum of w/lik p_c L_root,l -- per thread over the whole item
+    double wsub[SUBST ? 16 : 1], rsub[SUBST ? 4 : 1];
+    if (SUBST) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) wsub[e] = 0.0;
+#pragma unroll
+      for (int e = 0; e < 4; e++) rsub[e] = 0.0;
+    }
+    // wsub += sum_j scale_j (V^T t_j) (z_j)^T o Phi, Phi row-major at `phi` (this lane's category)
+    auto accumulate_subst = [&](const double (&t)[OePreBatch(K)][4], const double (&z)[OePreBatch(K)][4],
+                                const double (&scale)[OePreBatch(K)], const double* phi) {
+      double u[OePreBatch(K)][4];
+      MatTVecSharedK<OePreBatch(K)>(evec_smem, t, u);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        double row[4];
+        Load4(phi + 4 * k, row);
+#pragma unroll
+        for (int j = 0; j < OePreBatch(K); j++) {
+          const double su = scale[j] * u[j][k];
+#pragma unroll
+          for (int l = 0; l < 4; l++) wsub[SUBST ? k * 4 + l : 0] = fma(su * z[j][l], row[l], wsub[SUBST ? k * 4 + l : 0]);
+        }
+      }
+    };
     for (int tile = tile_begin; tile < tile_end; tile++) {
       const int64_t pat0 = p.pattern_begin + static_cast<int64_t>(tile) * kTilePatterns;
       double w[K];
@@ -681,8 +766,8 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
         } else {
           // ================ pre-order op + edge derivatives ================
           // operand layout: own P (an identity at the root), tip tables of a, tip tables of b
-          const double* const table_a = operand + kInnerPart;
-          const double* const table_b = table_a + (a_leaf ? 2 * kLeafPart : 0);
+          const double* const table_a = operand + kInnerPart + kPhiPart;
+          const double* const table_b = table_a + (a_leaf ? 2 * kLeafPart + kPhiPart : 0);
           const int next_children = ((flags & kNextALeaf) ? 0 : 1) + ((flags & kNextBLeaf) ? 0 : 1);
           // read-back order of two internal children: the post-order op's child order
           const bool swapped = flags & kArenaSwapped;
@@ -695,6 +780,7 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
             double(&top)[KP][4] = *reinterpret_cast<double(*)[KP][4]>(&cur[j0]);
             // ---- pre-order partial at this node: pp = P^T T
             double pp[KP][4];
+            double tv[SUBST ? KP : 1][4];  // T_v itself, for the substitution gradient of v's edge
             if (flags & kStackBefore) {
               const int s0 = record.y & 0xff;
               double x[KP][4];
@@ -705,8 +791,20 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
                 x[j][0] = v0.x, x[j][1] = v0.y, x[j][2] = v1.x, x[j][3] = v1.y;
               }
               MatTVecSharedK<KP>(operand + cat * kPStride, x, pp);
+              if (SUBST) {
+#pragma unroll
+                for (int j = 0; j < KP; j++)
+#pragma unroll
+                  for (int i = 0; i < 4; i++) tv[j][i] = x[j][i];
+              }
             } else {
               MatTVecSharedK<KP>(operand + cat * kPStride, top, pp);
+              if (SUBST) {
+#pragma unroll
+                for (int j = 0; j < KP; j++)
+#pragma unroll
+                  for (int i = 0; i < 4; i++) tv[j][i] = top[j][i];
+              }
             }
             // ---- evolved partials of both children
             double ya[KP][4], yb[KP][4];
@@ -767,6 +865,20 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
 #pragma unroll
               for (int j = 0; j < KP; j++) g_own = fma(scale[j], num[j], g_own);
             }
+            if (SUBST) {
+              // v's own edge: T_v and L_v = site (Phi is zero in the root's block)
+              double z[KP][4];
+              MatVecOe<KP>(ivec_smem, site, z);
+              accumulate_subst(*reinterpret_cast<const double(*)[KP][4]>(&tv[0]), z, scale,
+                               operand + kInnerPart + cat * kOePhiDoubles);
+              if (flags & kRoot) {
+#pragma unroll
+                for (int j = 0; j < KP; j++)
+#pragma unroll
+                  for (int l = 0; l < 4; l++)
+                    rsub[SUBST ? l : 0] = fma(scale[j] * cat_weight, site[j][l], rsub[SUBST ? l : 0]);
+              }
+            }
             // ---- the partials at the top of the children's edges: T_a (kept in cur), T_b
 #pragma unroll
             for (int j = 0; j < KP; j++)
@@ -781,6 +893,12 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
                 double d[4];
                 Load4(table_a + (C + cat) * kTipTableDoubles + tip_row(states_a, j0 + j), d);
                 g_a = fma(scale[j], Dot4(top[j], d), g_a);
+              }
+              if (SUBST) {
+                double z[KP][4];
+#pragma unroll
+                for (int j = 0; j < KP; j++) Load4(tip_z_smem + tip_row(states_a, j0 + j), z[j]);
+                accumulate_subst(top, z, scale, table_a + 2 * kLeafPart + cat * kOePhiDoubles);
               }
             }
             if (RESCALE) {
@@ -814,6 +932,12 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
                 double d[4];
                 Load4(table_b + (C + cat) * kTipTableDoubles + tip_row(states_b, j0 + j), d);
                 g_b = fma(scale[j], Dot4(yb[j], d), g_b);
+              }
+              if (SUBST) {
+                double z[KP][4];
+#pragma unroll
+                for (int j = 0; j < KP; j++) Load4(tip_z_smem + tip_row(states_b, j0 + j), z[j]);
+                accumulate_subst(yb, z, scale, table_b + 2 * kLeafPart + cat * kOePhiDoubles);
               }
             } else {
               const int s2 = (record.y >> 16) & 0xff;
@@ -878,6 +1002,19 @@ __global__ void __launch_bounds__(kThreads, OeMinBlocks(K, GRAD)) TreeWalkOeKern
     // one partial per warp, in lane order
     logl_acc = WarpSum(logl_acc);
     if (lane == 0) p.logl_partial[out_row] = logl_acc;
+    if (SUBST) {
+      double* const sums = p.subst_partial + out_row * kOeSubstSums;
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const double total = WarpSum(wsub[SUBST ? e : 0]);
+        if (lane == 0) sums[e] = total;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const double total = WarpSum(rsub[SUBST ? e : 0]);
+        if (lane == 0) sums[16 + e] = total;
+      }
+    }
   }
 }
 

@@ -160,6 +160,15 @@ class Engine:
         self.param_count = lib.sbnb_engine_param_count(handle)
         self.category_count = lib.sbnb_engine_category_count(handle)
 
+    def set_substitution_gradient(self, mode):
+        """'analytic' (default): exact d logL / d (substitution parameters) inside the
+        gradient sweep; 'fd': the reference's 16 central-difference log-likelihood
+        sweeps (fat_beagle.cpp:400-465)."""
+        modes = {"analytic": _capi.SUBSTITUTION_ANALYTIC, "fd": _capi.SUBSTITUTION_FINITE_DIFFERENCES}
+        if mode not in modes:
+            raise RuntimeError("substitution gradient mode must be 'analytic' or 'fd'.")
+        _capi.check(_capi.load().sbnb_engine_set_substitution_gradient(self._handle, modes[mode]))
+
     def close(self):
         if getattr(self, "_handle", None):
             _capi.load().sbnb_engine_destroy(self._handle)

@@ -367,3 +367,76 @@ def test_fasta_parsing_and_symbol_table(tmp_path):
         alignment.sequences_in_leaf_order(sequences, ["w"])
     with pytest.raises(RuntimeError):
         alignment.encode({"x": "ACZT"}, ["x"])
+
+
+def _stick_breaking(y, size):
+    x, stick = np.zeros(size), 1.0
+    for k in range(size - 1):
+        z = 1.0 / (1.0 + np.exp(-(y[k] - np.log(size - k - 1))))
+        x[k] = stick * z
+        stick -= x[k]
+    x[-1] = stick
+    return x
+
+
+def _stick_breaking_inverse(x):
+    size, y, total = len(x), np.zeros(len(x) - 1), 0.0
+    for k in range(size - 1):
+        z = x[k] / (1.0 - total)
+        y[k] = np.log(z / (1.0 - z)) + np.log(size - k - 1)
+        total += x[k]
+    return y
+
+
+@pytest.mark.parametrize("substitution", ["GTR", "HKY"])
+def test_analytic_substitution_derivatives_match_central_differences_of_p(substitution):
+    """Host part of the analytic substitution gradient: with
+    B = V^-1 dQ/dtheta V from sbnb_debug_substitution_derivatives,
+    d P(tau) / d theta = V (B o Phi(tau)) V^-1 must equal the central difference of P over the
+    reference's own perturbation (stick-breaking coordinates +/- delta, fat_beagle.cpp:400-465)."""
+    lib = _capi.load()
+    rates = np.array([0.05, 0.1, 0.15, 0.20, 0.25, 0.25])
+    freqs = np.array([0.1, 0.2, 0.3, 0.4])
+    kappa = 2.3
+    row = np.concatenate([rates, freqs]) if substitution == "GTR" else np.concatenate([freqs, [kappa]])
+    b, dfreqs, count = np.zeros(8 * 16), np.zeros(8 * 4), ctypes.c_int32()
+    _capi.check(lib.sbnb_debug_substitution_derivatives(substitution.encode(), b"constant", b"none",
+                                                        _capi.as_double_ptr(row), _capi.as_double_ptr(b),
+                                                        _capi.as_double_ptr(dfreqs), ctypes.byref(count)))
+    assert count.value == (8 if substitution == "GTR" else 4)
+    b, dfreqs = b.reshape(8, 4, 4), dfreqs.reshape(8, 4)
+    base = model_tables(substitution, "constant", row)
+
+    def perturbed(index, step):
+        """The row with gradient coordinate `index` moved by `step`."""
+        r, f, k = rates.copy(), freqs.copy(), kappa
+        if substitution == "GTR" and index < 5:
+            y = _stick_breaking_inverse(r)
+            y[index] += step
+            r = _stick_breaking(y, 6)
+        elif substitution == "HKY" and index == 0:
+            k += step
+        else:
+            y = _stick_breaking_inverse(f)
+            y[index - (5 if substitution == "GTR" else 1)] += step
+            f = _stick_breaking(y, 4)
+        return np.concatenate([r, f]) if substitution == "GTR" else np.concatenate([f, [k]])
+
+    def p_of(tables, tau):
+        return tables["evec"] @ np.diag(np.exp(tables["eval"] * tau)) @ tables["ivec"]
+
+    delta = 1e-6
+    lam = base["eval"]
+    for tau in (1e-3, 0.07, 0.9, 6.0):
+        diff = lam[:, None] - lam[None, :]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            phi = np.where(np.abs(diff) > 1e-12,
+                           (np.exp(lam[:, None] * tau) - np.exp(lam[None, :] * tau)) / diff,
+                           tau * np.exp(lam[:, None] * tau) * np.ones((4, 4)))
+        for index in range(count.value):
+            analytic = base["evec"] @ (b[index] * phi) @ base["ivec"]
+            up = model_tables(substitution, "constant", perturbed(index, +delta))
+            down = model_tables(substitution, "constant", perturbed(index, -delta))
+            numeric = (p_of(up, tau) - p_of(down, tau)) / (2 * delta)
+            assert np.max(np.abs(analytic - numeric)) < 1e-8, (tau, index)
+            assert np.allclose(dfreqs[index], (up["freqs"] - down["freqs"]) / (2 * delta), atol=1e-9)

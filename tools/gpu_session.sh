@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-(timeout 1200 python -m pytest tests/test_integration_gpu.py -x -q) > gpurun_out/s14_pytest.log 2>&1; tail -12 gpurun_out/s14_pytest.log
+(timeout 1500 python -m pytest tests -m gpu -x -q) > gpurun_out/s17_pytest.log 2>&1; tail -6 gpurun_out/s17_pytest.log
