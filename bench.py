@@ -386,7 +386,7 @@ def small_problem_leg(local_rank):
                    "are not)", "cpu": f"oracle port (oracle/phylo_oracle.cpp) on {cores} threads, median of 5",
            "cases": []}
     cases = [("JC69 log_likelihoods (configs[0])", "ds1_100_topologies_jc69", False),
-             ("GTR+weibull4 phylo_gradients: branch + site + substitution (16 FD sweeps) (configs[1])",
+             ("GTR+weibull4 phylo_gradients: logL + branch + site-model + substitution-model gradients (configs[1])",
               "ds1_100_topologies_gtr_weibull4", True)]
     for label, name, gradient in cases:
         with np.load(os.path.join(golden, name + ".npz"), allow_pickle=False) as data:

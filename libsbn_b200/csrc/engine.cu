@@ -12,6 +12,8 @@
 #include <exception>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -96,6 +98,8 @@ struct sbnb_engine {
   // points (which stage per call) neither cudaMallocs nor cudaFrees, and finds the
   // traversal programs of an unchanged topology set already on the device.
   sbnb_batch* spare = nullptr;
+  // resident CTAs per SM of every walk kernel this engine has launched: kernel -> (smem, CTAs)
+  std::unordered_map<const void*, std::pair<size_t, int>> occupancy;
 
   // Multi-GPU group (sbnb_engine_create_multi): this object is then only a front
   // for one child engine per device; see the "device groups" section below.
@@ -142,6 +146,22 @@ struct sbnb_batch {
   DeviceArray<double> results;  // [logl (vtree_count) | grad (T x N) | rgrad (T x N) | subst sums (T x 20)]
   // tiling of the last run
   int chunks = 1;
+  // One-call entry points on an unchanged topology set replay the launch sequence
+  // [matrices, walk(s), reduce, results -> host] as a CUDA graph (one per mode and
+  // rescaling flag), re-captured whenever a buffer it names has moved.
+  struct Graph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<uintptr_t> signature;
+    int kernels = 0;
+    bool warm = false;  // this very sequence has run eagerly since the programs were staged: buffers sized
+  };
+  Graph graphs[2][2];
+  int cache_hits = 0;  // consecutive Stage() calls that found the programs on the device
+  ~sbnb_batch() {
+    for (auto& row : graphs)
+      for (auto& graph : row)
+        if (graph.exec) cudaGraphExecDestroy(graph.exec);
+  }
 
   template <typename T>
   T* At(size_t offset) const {
@@ -197,16 +217,17 @@ LaunchPlan PlanAndLaunchOe(sbnb_engine* e, OeParams p, bool launch, int chunks_o
   // (SBNB_EXTRA_SMEM: development aid -- pads the request to lower the resident CTA count)
   const size_t smem =
       OeSmemBytes(C, K, GRAD, SUBST) + static_cast<size_t>(std::max(0, EnvInt("SBNB_EXTRA_SMEM", 0)));
-  static thread_local int cached_device = -1, cached_per_sm = 0;
-  static thread_local size_t cached_smem = 0;
-  if (cached_device != e->device || cached_smem != smem) {
+  // (attributes and occupancy of a kernel are asked for once per engine)
+  auto known = e->occupancy.find(reinterpret_cast<const void*>(kernel));
+  if (known == e->occupancy.end() || known->second.first != smem) {
+    int per_sm_now = 0;
     SBNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     SBNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
-    SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, kernel, kThreads, smem));
-    cached_device = e->device;
-    cached_smem = smem;
+    SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_now, kernel, kThreads, smem));
+    known = e->occupancy.insert_or_assign(reinterpret_cast<const void*>(kernel), std::make_pair(smem, per_sm_now)).first;
   }
+  const int cached_per_sm = known->second.second;
   const int per_sm = cached_per_sm;
   if (per_sm < 1) Fail(SBNB_ERR_CUDA, "TreeWalkOeKernel does not fit on an SM.");
   const int resident = per_sm * e->sm_count;
@@ -592,6 +613,10 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   int32_t* vtree_model = reinterpret_cast<int32_t*>(host + batch->vtree_model_at);
   int32_t* vtree_lengths = reinterpret_cast<int32_t*>(host + batch->vtree_lengths_at);
 
+  batch->cache_hits = cached ? batch->cache_hits + 1 : 0;
+  if (!cached)
+    for (auto& row : batch->graphs)
+      for (auto& graph : row) graph.warm = false;
   if (!cached) {
     // Programs: host schedule generation, then the records the kernels read.
     OeOp* ops = reinterpret_cast<OeOp*>(host + batch->ops_at);
@@ -725,7 +750,7 @@ void LaunchMatrices(sbnb_engine* e, sbnb_batch* b, double* operands, int64_t str
   e->launch_count++;
 }
 
-void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
+void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling, bool timed = true) {
   Require(mode == SBNB_MODE_LOG_LIKELIHOOD || mode == SBNB_MODE_BRANCH_GRADIENT, "Unknown mode.");
   SBNB_CUDA(cudaSetDevice(e->device));
   b->last_mode = mode;
@@ -783,12 +808,16 @@ void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
   p.operands = b->operands.get();
   p.operand_origin = 0;
   p.operand_stride = b->operand_stride;
-  const int ring = static_cast<int>(e->walk_runs++ % sbnb_engine::kWalkRing);
-  HarvestWalkTiming(e, ring);  // the slot about to be reused
-  SBNB_CUDA(cudaEventRecord(e->walk_begin[ring], s));
-  Dispatch(e, p, grad, rescaling, /*launch=*/true, chunks);
-  SBNB_CUDA(cudaEventRecord(e->walk_end[ring], s));
-  e->walk_pending[ring] = true;
+  if (timed) {
+    const int ring = static_cast<int>(e->walk_runs++ % sbnb_engine::kWalkRing);
+    HarvestWalkTiming(e, ring);  // the slot about to be reused
+    SBNB_CUDA(cudaEventRecord(e->walk_begin[ring], s));
+    Dispatch(e, p, grad, rescaling, /*launch=*/true, chunks);
+    SBNB_CUDA(cudaEventRecord(e->walk_end[ring], s));
+    e->walk_pending[ring] = true;
+  } else {
+    Dispatch(e, p, grad, rescaling, /*launch=*/true, chunks);
+  }
 
   if (fd_vtrees > 0) {
     e->fd_operands.Reserve(static_cast<size_t>(slice) * b->post_doubles);
@@ -819,41 +848,122 @@ void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling) {
   }
 }
 
+// How many doubles of the result array a fetch of these outputs copies.
+size_t FetchCount(const sbnb_engine* e, const sbnb_batch* b, bool grad, bool rgrad, bool subst) {
+  const bool was_grad = (b->last_mode == SBNB_MODE_BRANCH_GRADIENT);
+  const size_t vtrees = was_grad ? b->vtree_count : b->tree_count;
+  const size_t grad_count = static_cast<size_t>(b->tree_count) * b->node_count;
+  const bool rates = rgrad && e->padded_categories > 1;
+  if (subst) return b->vtree_count + 2 * grad_count + static_cast<size_t>(b->tree_count) * kOeSubstSums;
+  return (grad || rates) ? b->vtree_count + (rates ? 2 : 1) * grad_count : vtrees;
+}
+
+// Results that have landed in page-locked memory -> the caller's arrays.
+void Unpack(const sbnb_engine* e, const sbnb_batch* b, const double* landed, double* logl, double* grad,
+            double* rgrad, double* subst) {
+  const bool was_grad = (b->last_mode == SBNB_MODE_BRANCH_GRADIENT);
+  const size_t vtrees = was_grad ? b->vtree_count : b->tree_count;
+  const size_t grad_count = static_cast<size_t>(b->tree_count) * b->node_count;
+  if (logl) std::copy(landed, landed + vtrees, logl);
+  if (grad) std::copy(landed + b->vtree_count, landed + b->vtree_count + grad_count, grad);
+  if (rgrad) {
+    if (e->padded_categories > 1) {
+      std::copy(landed + b->vtree_count + grad_count, landed + b->vtree_count + 2 * grad_count, rgrad);
+    } else {
+      std::fill(rgrad, rgrad + grad_count, 0.0);
+    }
+  }
+  if (subst)
+    std::copy(landed + b->vtree_count + 2 * grad_count,
+              landed + b->vtree_count + 2 * grad_count + static_cast<size_t>(b->tree_count) * kOeSubstSums, subst);
+}
+
 void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rgrad, double* subst = nullptr) {
   SBNB_CUDA(cudaSetDevice(e->device));
   Require(b->last_mode >= 0, "sbnb_batch_fetch called before sbnb_batch_run.");
   const bool was_grad = (b->last_mode == SBNB_MODE_BRANCH_GRADIENT);
   Require(was_grad || (!grad && !rgrad), "No gradient available: the last run was a log-likelihood run.");
-  const size_t vtrees = was_grad ? b->vtree_count : b->tree_count;
-  const size_t grad_count = static_cast<size_t>(b->tree_count) * b->node_count;
+  if (subst) Require(was_grad && b->with_subst, "No substitution-gradient sums: the batch was not staged for them.");
   cudaStream_t s = e->stream;
-  if (b->tree_count > 0) {
-    // One copy of what is asked for into page-locked memory, then out to the caller's arrays.
-    const bool rates = rgrad && e->padded_categories > 1;
-    const size_t subst_count = static_cast<size_t>(b->tree_count) * kOeSubstSums;
-    if (subst) Require(was_grad && b->with_subst, "No substitution-gradient sums: the batch was not staged for them.");
-    const size_t count = subst ? b->vtree_count + 2 * grad_count + subst_count
-                               : ((grad || rates) ? b->vtree_count + (rates ? 2 : 1) * grad_count : vtrees);
-    e->landing.Reset(count * sizeof(double));
-    double* landed = e->landing.Take<double>(count);
-    SBNB_CUDA(cudaMemcpyAsync(landed, b->results.get(), count * sizeof(double), cudaMemcpyDeviceToHost, s));
-    e->d2h_bytes += count * sizeof(double);
+  if (b->tree_count == 0) {
     SBNB_CUDA(cudaStreamSynchronize(s));
-    if (logl) std::copy(landed, landed + vtrees, logl);
-    if (grad) std::copy(landed + b->vtree_count, landed + b->vtree_count + grad_count, grad);
-    if (rgrad) {
-      if (rates) {
-        std::copy(landed + b->vtree_count + grad_count, landed + b->vtree_count + 2 * grad_count, rgrad);
-      } else {
-        std::fill(rgrad, rgrad + grad_count, 0.0);
-      }
-    }
-    if (subst)
-      std::copy(landed + b->vtree_count + 2 * grad_count, landed + b->vtree_count + 2 * grad_count + subst_count,
-                subst);
-  } else {
-    SBNB_CUDA(cudaStreamSynchronize(s));
+    return;
   }
+  // One copy of what is asked for into page-locked memory, then out to the caller's arrays.
+  const size_t count = FetchCount(e, b, grad != nullptr, rgrad != nullptr, subst != nullptr);
+  e->landing.Reset(count * sizeof(double));
+  double* landed = e->landing.Take<double>(count);
+  SBNB_CUDA(cudaMemcpyAsync(landed, b->results.get(), count * sizeof(double), cudaMemcpyDeviceToHost, s));
+  e->d2h_bytes += count * sizeof(double);
+  SBNB_CUDA(cudaStreamSynchronize(s));
+  Unpack(e, b, landed, logl, grad, rgrad, subst);
+}
+
+// Run + Fetch of the one-call entry points.  Once the same topology set has come in
+// three times in a row (programs cached on the device, the same sequence run eagerly once), the launch
+// sequence is captured into a CUDA graph and replayed: one launch call instead of
+// 4-6 launches, 2 event records and a copy (the small-problem regime of
+// BASELINE.json configs[0..1], where a call is tens of microseconds).
+void RunAndFetch(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling, double* logl, double* grad,
+                 double* rgrad, double* subst = nullptr) {
+  static const bool graphs_enabled = EnvInt("SBNB_GRAPHS", 1) != 0;
+  sbnb_batch::Graph& graph = b->graphs[mode == SBNB_MODE_BRANCH_GRADIENT ? 1 : 0][rescaling ? 1 : 0];
+  if (!graphs_enabled || b->tree_count == 0 || b->cache_hits < 1 || !graph.warm) {
+    Run(e, b, mode, rescaling);
+    Fetch(e, b, logl, grad, rgrad, subst);
+    graph.warm = b->cache_hits >= 1;  // (an eager run on cached programs: the next one may be captured)
+    return;
+  }
+  SBNB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  b->last_mode = mode;
+  const size_t count = FetchCount(e, b, grad != nullptr, rgrad != nullptr, subst != nullptr);
+  e->landing.Reset(count * sizeof(double));
+  double* landed = e->landing.Take<double>(count);
+  auto signature = [&] {
+    return std::vector<uintptr_t>{
+        reinterpret_cast<uintptr_t>(b->input.get()),        reinterpret_cast<uintptr_t>(b->operands.get()),
+        reinterpret_cast<uintptr_t>(b->results.get()),      reinterpret_cast<uintptr_t>(b->logl_partial.get()),
+        reinterpret_cast<uintptr_t>(b->grad_partial.get()), reinterpret_cast<uintptr_t>(b->rgrad_partial.get()),
+        reinterpret_cast<uintptr_t>(b->subst_partial.get()), reinterpret_cast<uintptr_t>(e->stack.get()),
+        reinterpret_cast<uintptr_t>(e->stack_exps.get()),   reinterpret_cast<uintptr_t>(e->arena.get()),
+        reinterpret_cast<uintptr_t>(e->fd_operands.get()),  reinterpret_cast<uintptr_t>(e->tips.get()),
+        reinterpret_cast<uintptr_t>(e->weights.get()),      reinterpret_cast<uintptr_t>(landed),
+        static_cast<uintptr_t>(count),                      static_cast<uintptr_t>(b->vtree_count),
+        static_cast<uintptr_t>(b->with_subst),              static_cast<uintptr_t>(e->range_end - e->range_begin),
+        static_cast<uintptr_t>(b->slots)};
+  };
+  if (graph.exec == nullptr || graph.signature != signature()) {
+    if (graph.exec) {
+      cudaGraphExecDestroy(graph.exec);
+      graph.exec = nullptr;
+    }
+    // (the previous two calls ran this very sequence: every buffer has its size, so
+    //  nothing below allocates while the stream is capturing)
+    const int64_t launches_before = e->launch_count;
+    SBNB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    cudaGraph_t recorded = nullptr;
+    try {
+      Run(e, b, mode, rescaling, /*timed=*/false);
+      SBNB_CUDA(cudaMemcpyAsync(landed, b->results.get(), count * sizeof(double), cudaMemcpyDeviceToHost, s));
+    } catch (...) {
+      cudaStreamEndCapture(s, &recorded);
+      if (recorded) cudaGraphDestroy(recorded);
+      throw;
+    }
+    SBNB_CUDA(cudaStreamEndCapture(s, &recorded));
+    graph.kernels = static_cast<int>(e->launch_count - launches_before);
+    e->launch_count = launches_before;
+    const cudaError_t status = cudaGraphInstantiate(&graph.exec, recorded, 0);
+    cudaGraphDestroy(recorded);
+    SBNB_CUDA(status);
+    graph.signature = signature();  // (the capture itself may have moved nothing; taken after it on purpose)
+  }
+  SBNB_CUDA(cudaGraphLaunch(graph.exec, s));
+  e->launch_count += graph.kernels;
+  e->d2h_bytes += count * sizeof(double);
+  SBNB_CUDA(cudaStreamSynchronize(s));
+  Unpack(e, b, landed, logl, grad, rgrad, subst);
 }
 
 RootedView ViewOf(const sbnb_tree_batch* trees, int t, int n) {
@@ -927,8 +1037,7 @@ void LogLikelihoods(sbnb_engine* e, const sbnb_tree_batch* trees, const double* 
   Require(trees != nullptr, "NULL tree batch.");
   Require(out != nullptr || trees->tree_count == 0, "NULL output.");
   auto batch = Stage(e, trees, params, rooted_semantics, false, /*slide_root=*/false);
-  Run(e, batch.get(), SBNB_MODE_LOG_LIKELIHOOD, rescaling);
-  Fetch(e, batch.get(), out, nullptr, nullptr);
+  RunAndFetch(e, batch.get(), SBNB_MODE_LOG_LIKELIHOOD, rescaling, out, nullptr, nullptr);
   if (add_jacobian) {
     Require(trees->tree_count == 0 || (trees->node_heights && trees->node_bounds),
             "Rooted log likelihoods need node_heights and node_bounds.");
@@ -1016,11 +1125,11 @@ void Gradients(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   const bool wanted = coords > 0 && out->substitution_model != nullptr;
   const bool analytic = wanted && e->substitution_mode == SBNB_SUBSTITUTION_ANALYTIC;
   auto batch = Stage(e, trees, params, rooted, wanted && !analytic, /*slide_root=*/true, analytic);
-  Run(e, batch.get(), SBNB_MODE_BRANCH_GRADIENT, rescaling);
   const int T = trees->tree_count, N = 2 * e->taxon_count - 1;
   std::vector<double> logl(batch->vtree_count), grad(static_cast<size_t>(T) * N),
       rgrad(static_cast<size_t>(T) * N), subst(analytic ? static_cast<size_t>(T) * kOeSubstSums : 0);
-  Fetch(e, batch.get(), logl.data(), grad.data(), rgrad.data(), analytic && T > 0 ? subst.data() : nullptr);
+  RunAndFetch(e, batch.get(), SBNB_MODE_BRANCH_GRADIENT, rescaling, logl.data(), grad.data(), rgrad.data(),
+              analytic && T > 0 ? subst.data() : nullptr);
   FinishGradients(e->spec, e->taxon_count, trees, rooted, batch->fd_coords, logl.data(), grad.data(),
                   rgrad.data(), out, &batch->programs, params, analytic && T > 0 ? subst.data() : nullptr);
 }

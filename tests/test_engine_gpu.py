@@ -373,3 +373,32 @@ def test_analytic_substitution_gradient_matches_finite_differences(substitution,
     assert a.shape == (batch.tree_count, 8 if substitution == "GTR" else 4)
     assert np.max(np.abs(a - d)) < 2 * fd_noise(logl), (a[0], d[0])
     assert np.max(np.abs(a - d) / np.max(np.abs(d), axis=1, keepdims=True)) < 1e-4
+
+
+def test_repeated_calls_on_unchanged_topologies_replay_a_graph(oracle):
+    """Variational inference re-evaluates the same trees with new branch lengths and
+    parameters (vip/burrito.py:84-117): the traversal programs stay on the device and
+    from the third call on the launch sequence is replayed as a CUDA graph.  Every call
+    must still see the new lengths / parameters."""
+    fx = load_fixture("ds1_gtr_weibull4")
+    engine = engine_of(fx)
+    rng = np.random.default_rng(3)
+    launches = []
+    for call in range(6):
+        lengths = fx["branch_lengths"] * rng.uniform(0.5, 1.5, size=fx["branch_lengths"].shape)
+        lengths[:, -1] = 0.0
+        params = fx["params"].copy()
+        params[:, -1] = rng.uniform(0.3, 1.2)  # the Weibull shape
+        batch = sbn.TreeBatch(fx["parent_ids"], lengths)
+        rescaling = bool(call % 2 == 0) if call >= 4 else True
+        before = engine.launch_count
+        logl = engine.log_likelihoods(batch, params, rescaling)
+        got = engine.gradients(batch, params, rescaling)
+        launches.append(engine.launch_count - before)
+        want = oracle.gradients(fx["substitution"], fx["site"], fx["patterns"], fx["weights"], fx["parent_ids"],
+                                lengths, params, rescaling=rescaling)
+        assert rel(logl, want["log_likelihood"]) < LOGL_RTOL
+        assert rel([g.log_likelihood for g in got], want["log_likelihood"]) < LOGL_RTOL
+        assert grad_rel(stack(got, "branch_lengths"), want["branch"]) < GRAD_RTOL
+        assert np.max(np.abs(stack(got, "substitution_model") - want["substitution_model"])) < fd_noise(logl)
+    assert len(set(launches)) == 1  # kernels counted alike, launched eagerly or replayed
