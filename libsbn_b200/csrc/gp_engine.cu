@@ -40,6 +40,8 @@
 
 namespace cg = cooperative_groups;
 
+constexpr int kGpProgramSmemWords = 8192;
+
 namespace sbnb {
 
 namespace {
@@ -203,6 +205,16 @@ struct Reducer {
 
 __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const GpParams p) {
   __shared__ double reduce_smem[32][4];
+  // The op program is a dependency chain: every op starts by reading its own words.  A
+  // program of up to kGpProgramSmemWords words (the DS1 DAG's sweeps are ~5.5 k) is staged
+  // in shared memory once, so that read is an LDS instead of a global round trip per op.
+  __shared__ int32_t program_smem[kGpProgramSmemWords];
+  const int32_t* program = p.program;
+  if (p.word_count <= kGpProgramSmemWords) {
+    for (int64_t w = threadIdx.x; w < p.word_count; w += blockDim.x) program_smem[w] = p.program[w];
+    __syncthreads();
+    program = program_smem;
+  }
   Reducer reduce{p, gridDim.x > 1, 0, reduce_smem};
   const int64_t P = p.pattern_count;
   const int64_t first = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -238,10 +250,10 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
 
   int64_t pc = 0;
   while (pc < p.word_count) {
-    const int opcode = p.program[pc];
+    const int opcode = program[pc];
     switch (opcode) {
       case SBNB_GP_ZERO_PLV: {  // gp_engine.cpp:48-51
-        const int dest = p.program[pc + 1];
+        const int dest = program[pc + 1];
         const double zero[4] = {0.0, 0.0, 0.0, 0.0};
         for (int64_t k = first; k < P; k += stride) StoreState(plv(dest), k, zero);
         counts[dest] = 0;
@@ -249,7 +261,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         break;
       }
       case SBNB_GP_SET_TO_STATIONARY: {  // gp_engine.cpp:53-62
-        const int dest = p.program[pc + 1], root = p.program[pc + 2];
+        const int dest = program[pc + 1], root = program[pc + 2];
         const double prior = p.q[root];
         const double x[4] = {prior * p.freqs[0], prior * p.freqs[1], prior * p.freqs[2], prior * p.freqs[3]};
         for (int64_t k = first; k < P; k += stride) StoreState(plv(dest), k, x);
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         break;
       }
       case SBNB_GP_INCREMENT_WITH_EVOLVED: {  // gp_engine.cpp:64-82
-        const int dest = p.program[pc + 1], gpcsp = p.program[pc + 2], src = p.program[pc + 3];
+        const int dest = program[pc + 1], gpcsp = program[pc + 2], src = program[pc + 3];
         const int difference = counts[src] - counts[dest];
         if (difference < 0) {
           fault(kGpFaultDestRescaling, pc);
@@ -281,7 +293,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         break;
       }
       case SBNB_GP_MULTIPLY: {  // gp_engine.cpp:111-117 + RescalePLVIfNeeded 298-320
-        const int dest = p.program[pc + 1], src1 = p.program[pc + 2], src2 = p.program[pc + 3];
+        const int dest = program[pc + 1], src1 = program[pc + 2], src2 = program[pc + 3];
         int count = counts[src1] + counts[src2];
         double values[3] = {0.0, 0.0, 0.0};  // max entry, max of -entry, non-finite flag
         for (int64_t k = first; k < P; k += stride) {
@@ -331,7 +343,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         break;
       }
       case SBNB_GP_LIKELIHOOD: {  // gp_engine.cpp:119-123, gp_engine.hpp:198-206
-        const int dest = p.program[pc + 1], child = p.program[pc + 2], parent = p.program[pc + 3];
+        const int dest = program[pc + 1], child = program[pc + 2], parent = program[pc + 3];
         double m[16];
         TransitionMatrix(p, p.branch_lengths[dest], false, m);
         const double count_log = static_cast<double>(counts[parent]) * p.log_threshold +
@@ -347,7 +359,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         break;
       }
       case SBNB_GP_OPTIMIZE_BRANCH_LENGTH: {  // gp_engine.cpp:326-345, optimization.hpp:10-115
-        const int leafward = p.program[pc + 1], rootward = p.program[pc + 2], gpcsp = p.program[pc + 3];
+        const int leafward = program[pc + 1], rootward = program[pc + 2], gpcsp = program[pc + 3];
         const double count_log = static_cast<double>(counts[rootward]) * p.log_threshold +
                                  static_cast<double>(counts[leafward]) * p.log_threshold;
         auto f = [&](double log_branch_length) -> double {
@@ -427,7 +439,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         break;
       }
       case SBNB_GP_UPDATE_SBN_PROBABILITIES: {  // gp_engine.cpp:136-153
-        const int start = p.program[pc + 1], stop = p.program[pc + 2];
+        const int start = program[pc + 1], stop = program[pc + 2];
         const int length = stop - start;
         if (length == 1) {
           __syncthreads();  // lagging warps may still be reading q in an older op
@@ -478,7 +490,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         break;
       }
       case SBNB_GP_INCREMENT_MARGINAL: {  // gp_engine.cpp:88-109
-        const int stationary = p.program[pc + 1], rootsplit = p.program[pc + 2], leafward = p.program[pc + 3];
+        const int stationary = program[pc + 1], rootsplit = program[pc + 2], leafward = program[pc + 3];
         if (counts[stationary] != 0) {
           fault(kGpFaultRescaledStationary, pc);
           return;
@@ -498,9 +510,9 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         break;
       }
       case SBNB_GP_PREP_FOR_MARGINALIZATION: {  // gp_engine.cpp:155-165
-        const int dest = p.program[pc + 1], src_count = p.program[pc + 2];
-        int minimum = counts[p.program[pc + 3]];
-        for (int i = 1; i < src_count; i++) minimum = min(minimum, counts[p.program[pc + 3 + i]]);
+        const int dest = program[pc + 1], src_count = program[pc + 2];
+        int minimum = counts[program[pc + 3]];
+        for (int i = 1; i < src_count; i++) minimum = min(minimum, counts[program[pc + 3 + i]]);
         counts[dest] = minimum;
         pc += 3 + src_count;
         break;

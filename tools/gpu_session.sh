@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-(timeout 1500 python -m pytest tests -m gpu -x -q) > gpurun_out/s18_pytest.log 2>&1; tail -8 gpurun_out/s18_pytest.log
+python tools/gp_bench.py 2>&1 | tail -4 | cut -c1-700 | tee gpurun_out/r02_gp_bench_ds1.jsonl
+(timeout 900 python -m pytest tests/test_gp_gpu.py tests/test_integration_gpu.py -x -q) 2>&1 | tail -3
