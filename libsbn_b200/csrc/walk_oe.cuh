@@ -314,8 +314,14 @@ __global__ void PeerSumKernel(double* __restrict__ out, PeerPointers peers, int3
 }
 
 
-__host__ __device__ constexpr int OeStages(int C) { return C >= 8 ? 4 : 8; }  // operand ring depth
-__host__ __device__ constexpr int OePrefetchOps(int C) { return OeStages(C) / 2; }
+#ifndef SBNB_OE_STAGES
+#define SBNB_OE_STAGES 8
+#endif
+#ifndef SBNB_OE_PREFETCH
+#define SBNB_OE_PREFETCH (SBNB_OE_STAGES / 2)
+#endif
+__host__ __device__ constexpr int OeStages(int C) { return C >= 8 ? 4 : SBNB_OE_STAGES; }  // operand ring depth
+__host__ __device__ constexpr int OePrefetchOps(int C) { return C >= 8 ? 2 : SBNB_OE_PREFETCH; }
 __host__ __device__ constexpr int OeGroup(int C) { return kThreads / C; }  // patterns per j-slab
 __host__ __device__ constexpr int OeTilePatterns(int C, int K) { return OeGroup(C) * K; }
 __host__ __device__ constexpr int OeTipBytes(int C, int K) { return (OeTilePatterns(C, K) + 15) / 16 * 16; }

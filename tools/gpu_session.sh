@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python tools/gp_bench.py 2>&1 | tail -4 | cut -c1-700 | tee gpurun_out/r02_gp_bench_ds1.jsonl
-(timeout 900 python -m pytest tests/test_gp_gpu.py tests/test_integration_gpu.py -x -q) 2>&1 | tail -3
+(time python bench.py --impl reference --steps 3 --warmup 1) > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_ref.err; tail -c 200 gpurun_out/r02_ref.err
+(time python bench.py) > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; tail -c 300 gpurun_out/r02_bench.err; wc -c gpurun_out/r02_bench.json
