@@ -176,9 +176,14 @@ enum {
 
 enum {
   SBNB_STAGE_ROOTED = 1,          /* RootedTree semantics: branch lengths scaled by rates */
-  SBNB_STAGE_SUBSTITUTION_FD = 2  /* also stage the 2 x (5+3) perturbed models of the
+  SBNB_STAGE_SUBSTITUTION_FD = 2, /* also stage the 2 x (5+3) perturbed models of the
                                      finite-difference substitution gradient
                                      (fat_beagle.cpp:400-465) as extra logL-only evaluations */
+  SBNB_STAGE_SUBSTITUTION_ANALYTIC = 4 /* gradient runs also accumulate the 20 sums per tree of
+                                     the analytic substitution gradient (see
+                                     sbnb_engine_set_substitution_gradient); fetched with
+                                     sbnb_batch_fetch_substitution_sums, they follow the rate
+                                     gradients in the device result array */
 };
 
 /* Builds the per-tree traversal programs and eigen-systems on the host and
@@ -197,6 +202,10 @@ int sbnb_batch_run(sbnb_engine* engine, sbnb_batch* batch, int32_t mode, int32_t
  * NULL pointers are skipped. */
 int sbnb_batch_fetch(sbnb_engine* engine, sbnb_batch* batch, double* log_likelihoods,
                      double* branch_gradients, double* rate_gradients);
+/* The analytic substitution-gradient sums of the last gradient run of a batch staged with
+ * SBNB_STAGE_SUBSTITUTION_ANALYTIC: [T][20] = W (16, row-major) then R (4).  Sums over site
+ * patterns: ranks that each hold a pattern range add them like the other raw results. */
+int sbnb_batch_fetch_substitution_sums(sbnb_engine* engine, sbnb_batch* batch, double* sums);
 /* Device addresses of the raw result arrays sbnb_batch_fetch copies out
  * (fp64: [evaluation_count], [T][2n-1], [T][2n-1]), valid until the batch is
  * destroyed.  For site-pattern sharding: the ranks sum-all-reduce these in
@@ -249,6 +258,14 @@ int sbnb_finish_gradients(const char* substitution, const char* site, const char
                           int32_t with_substitution_fd, const double* log_likelihoods,
                           const double* branch_gradients, const double* rate_gradients,
                           const sbnb_gradient_out* out);
+/* The same host tail for a batch staged with SBNB_STAGE_SUBSTITUTION_ANALYTIC: the
+ * "substitution_model" block is < W, V^-1 dQ/dtheta V > + d pi/d theta . R from the (reduced)
+ * substitution sums and the parameter rows; everything else as sbnb_finish_gradients. */
+int sbnb_finish_gradients_analytic(const char* substitution, const char* site, const char* clock,
+                                   int32_t taxon_count, const sbnb_tree_batch* trees, int32_t rooted,
+                                   const double* params, const double* log_likelihoods,
+                                   const double* branch_gradients, const double* rate_gradients,
+                                   const double* substitution_sums, const sbnb_gradient_out* out);
 /* Adds the log-determinant Jacobian of the height-ratio transform
  * (fat_beagle.cpp:82-94) to already reduced rooted log-likelihoods, in place. */
 int sbnb_finish_log_likelihoods_rooted(int32_t taxon_count, const sbnb_tree_batch* trees,

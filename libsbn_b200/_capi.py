@@ -80,6 +80,11 @@ SIGNATURES = {
     "sbnb_batch_fetch": (_c.c_int, [_c.c_void_p, _c.c_void_p, _P(_c.c_double), _P(_c.c_double),
                                     _P(_c.c_double)]),
     "sbnb_batch_device_results": (_c.c_int, [_c.c_void_p, _P(_c.c_void_p), _P(_c.c_void_p), _P(_c.c_void_p)]),
+    "sbnb_batch_fetch_substitution_sums": (_c.c_int, [_c.c_void_p, _c.c_void_p, _P(_c.c_double)]),
+    "sbnb_finish_gradients_analytic": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int32,
+                                                  _P(TreeBatchStruct), _c.c_int32, _P(_c.c_double), _P(_c.c_double),
+                                                  _P(_c.c_double), _P(_c.c_double), _P(_c.c_double),
+                                                  _P(GradientOutStruct)]),
     "sbnb_finish_gradients": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_char_p, _c.c_int32, _P(TreeBatchStruct),
                                          _c.c_int32, _c.c_int32, _P(_c.c_double), _P(_c.c_double),
                                          _P(_c.c_double), _P(GradientOutStruct)]),
@@ -135,6 +140,8 @@ MODE_LOG_LIKELIHOOD = 0
 MODE_BRANCH_GRADIENT = 1
 STAGE_ROOTED = 1
 STAGE_SUBSTITUTION_FD = 2
+STAGE_SUBSTITUTION_ANALYTIC = 4
+SUBSTITUTION_SUMS = 20
 SHARD_TREES = 0
 SHARD_PATTERNS = 1
 SUBSTITUTION_ANALYTIC = 0

@@ -1510,8 +1510,11 @@ int sbnb_batch_stage(sbnb_engine* engine, const sbnb_tree_batch* trees, const do
     // (unrooted batches are staged with the root slid as the reference's Gradient does:
     //  a no-op for trifurcating input; for bifurcating input the log-likelihood is the
     //  same by the pulley principle)
+    Require(!((stage_flags & SBNB_STAGE_SUBSTITUTION_FD) && (stage_flags & SBNB_STAGE_SUBSTITUTION_ANALYTIC)),
+            "A batch is staged for one substitution-gradient method.");
     *out = Stage(engine, trees, params, (stage_flags & SBNB_STAGE_ROOTED) != 0,
-                 (stage_flags & SBNB_STAGE_SUBSTITUTION_FD) != 0, /*slide_root=*/true)
+                 (stage_flags & SBNB_STAGE_SUBSTITUTION_FD) != 0, /*slide_root=*/true,
+                 (stage_flags & SBNB_STAGE_SUBSTITUTION_ANALYTIC) != 0 && engine->spec.SubstitutionGradientSize() > 0)
                .release();
   });
 }
@@ -1530,6 +1533,39 @@ int sbnb_batch_fetch(sbnb_engine* engine, sbnb_batch* batch, double* log_likelih
     Require(engine && batch, "NULL argument.");
     RequireSingleDevice(engine);
     Fetch(engine, batch, log_likelihoods, branch_gradients, rate_gradients);
+  });
+}
+
+int sbnb_batch_fetch_substitution_sums(sbnb_engine* engine, sbnb_batch* batch, double* sums) {
+  return Guard([&] {
+    Require(engine && batch && sums, "NULL argument.");
+    RequireSingleDevice(engine);
+    Fetch(engine, batch, nullptr, nullptr, nullptr, sums);
+  });
+}
+
+int sbnb_finish_gradients_analytic(const char* substitution, const char* site, const char* clock,
+                                   int32_t taxon_count, const sbnb_tree_batch* trees, int32_t rooted,
+                                   const double* params, const double* log_likelihoods,
+                                   const double* branch_gradients, const double* rate_gradients,
+                                   const double* substitution_sums, const sbnb_gradient_out* out) {
+  return Guard([&] {
+    Require(substitution && site && clock, "NULL model specification string.");
+    Require(trees != nullptr, "NULL tree batch.");
+    Require(taxon_count >= 3, "Need at least 3 taxa.");
+    const ModelSpec spec = ModelSpec::Parse(substitution, site, clock);
+    Require(trees->tree_count == 0 || (trees->parent_ids && trees->branch_lengths),
+            "NULL parent_ids / branch_lengths.");
+    Require(trees->tree_count == 0 || (log_likelihoods && branch_gradients),
+            "NULL log_likelihoods / branch_gradients.");
+    Require(spec.category_count == 1 || trees->tree_count == 0 || rate_gradients != nullptr,
+            "rate_gradients are required for a multi-category site model.");
+    Require(spec.param_count == 0 || trees->tree_count == 0 || params != nullptr,
+            "NULL phylo model parameter matrix.");
+    Require(!rooted || trees->tree_count == 0 || trees->rates != nullptr,
+            "Rooted evaluation needs per-branch rates (RootedTree::rates_).");
+    FinishGradients(spec, taxon_count, trees, rooted != 0, 0, log_likelihoods, branch_gradients, rate_gradients,
+                    out, nullptr, params, spec.SubstitutionGradientSize() > 0 ? substitution_sums : nullptr);
   });
 }
 

@@ -8,6 +8,7 @@ and return one value / one PhyloGradient per tree; failures raise RuntimeError
 (the reference's Failwith).  Trees are passed in flat form (`TreeBatch`).
 """
 import ctypes
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional
 
@@ -111,6 +112,13 @@ class StagedBatch:
                                          _capi.as_double_ptr(grad), _capi.as_double_ptr(rgrad)))
         return (logl, grad, rgrad) if gradients else logl
 
+    def fetch_substitution_sums(self):
+        """[T][20] sums of the analytic substitution gradient (batch staged for them)."""
+        sums = np.empty((self.tree_count, _capi.SUBSTITUTION_SUMS))
+        _capi.check(_capi.load().sbnb_batch_fetch_substitution_sums(self._engine._handle, self._handle,
+                                                                    _capi.as_double_ptr(sums)))
+        return sums
+
     def algorithmic_bytes(self, mode):
         return _capi.load().sbnb_batch_algorithmic_bytes(self._handle, mode)
 
@@ -157,6 +165,7 @@ class Engine:
         self._handle = handle
         self.device = device
         self.device_count = lib.sbnb_engine_device_count(handle)
+        self.substitution_gradient_mode = "fd" if os.environ.get("SBNB_SUBSTITUTION_GRADIENT") == "fd" else "analytic"
         self.param_count = lib.sbnb_engine_param_count(handle)
         self.category_count = lib.sbnb_engine_category_count(handle)
 
@@ -168,6 +177,7 @@ class Engine:
         if mode not in modes:
             raise RuntimeError("substitution gradient mode must be 'analytic' or 'fd'.")
         _capi.check(_capi.load().sbnb_engine_set_substitution_gradient(self._handle, modes[mode]))
+        self.substitution_gradient_mode = mode
 
     def close(self):
         if getattr(self, "_handle", None):
@@ -262,9 +272,10 @@ class Engine:
         return results
 
     # -- staged form -------------------------------------------------------------
-    def stage(self, trees, params=None, rooted=False, substitution_fd=False):
+    def stage(self, trees, params=None, rooted=False, substitution_fd=False, substitution_analytic=False):
         params = self._params(params, trees.tree_count)
-        flags = (_capi.STAGE_ROOTED if rooted else 0) | (_capi.STAGE_SUBSTITUTION_FD if substitution_fd else 0)
+        flags = (_capi.STAGE_ROOTED if rooted else 0) | (_capi.STAGE_SUBSTITUTION_FD if substitution_fd else 0) | \
+            (_capi.STAGE_SUBSTITUTION_ANALYTIC if substitution_analytic else 0)
         handle = ctypes.c_void_p()
         struct = trees.as_struct()
         _capi.check(_capi.load().sbnb_batch_stage(self._handle, ctypes.byref(struct),

@@ -189,6 +189,39 @@ def finish_gradients(specification, taxon_count, trees, rooted, with_substitutio
                           {k: v[t].copy() for k, v in buffers.items() if k != "log_likelihood"}) for t in range(T)]
 
 
+def finish_gradients_analytic(specification, taxon_count, trees, rooted, params, log_likelihoods,
+                              branch_gradients, rate_gradients, substitution_sums, category_count):
+    """sbnb_finish_gradients_analytic: raw (already reduced) sums, among them the [T][20]
+    substitution sums -> PhyloGradients with an exact "substitution_model" block.  Host only."""
+    lib = _capi.load()
+    T, n = trees.tree_count, taxon_count
+    size = {"GTR": 8, "HKY": 4}.get(specification.substitution, 0)
+    buffers = {"log_likelihood": np.zeros(T)}
+    if rooted:
+        buffers["ratios_root_height"] = np.zeros((T, n - 1))
+        buffers["clock_model"] = np.zeros((T, trees.rate_count))
+    else:
+        buffers["branch_lengths"] = np.zeros((T, 2 * n - 1))
+    if size:
+        buffers["substitution_model"] = np.zeros((T, size))
+    if category_count > 1:
+        buffers["site_model"] = np.zeros((T, 1))
+    out = _capi.GradientOutStruct()
+    for key, value in buffers.items():
+        setattr(out, key, _capi.as_double_ptr(value))
+    struct = trees.as_struct()
+    as_array = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    params, log_likelihoods, branch_gradients = as_array(params), as_array(log_likelihoods), as_array(branch_gradients)
+    rate_gradients, substitution_sums = as_array(rate_gradients), as_array(substitution_sums)
+    _capi.check(lib.sbnb_finish_gradients_analytic(
+        specification.substitution.encode(), specification.site.encode(), specification.clock.encode(), n,
+        ctypes.byref(struct), int(rooted), _capi.as_double_ptr(params), _capi.as_double_ptr(log_likelihoods),
+        _capi.as_double_ptr(branch_gradients), _capi.as_double_ptr(rate_gradients),
+        _capi.as_double_ptr(substitution_sums), ctypes.byref(out)))
+    return [PhyloGradient(float(buffers["log_likelihood"][t]),
+                          {k: v[t].copy() for k, v in buffers.items() if k != "log_likelihood"}) for t in range(T)]
+
+
 def finish_log_likelihoods_rooted(taxon_count, trees, log_likelihoods):
     """sbnb_finish_log_likelihoods_rooted: + log-det Jacobian (fat_beagle.cpp:82-94), in place."""
     struct = trees.as_struct()
@@ -215,8 +248,10 @@ class PatternShardedEngine:
             if self.world > 1:
                 self.engine.set_pattern_range(self.begin, self.end)
 
-    def _reduce(self, staged, arrays_wanted):
-        """All-reduce of the raw result arrays of a finished run, then fetch."""
+    def _reduce(self, staged, arrays_wanted, substitution_sums=False):
+        """All-reduce of the raw result arrays of a finished run, then fetch
+        (arrays_wanted: 1 = log-likelihoods, 3 = + edge and rate derivatives;
+        substitution_sums: + the [T][20] sums of the analytic substitution gradient)."""
         lib = _capi.load()
         if self.world > 1 and self.backend == "nccl":
             import torch
@@ -226,7 +261,9 @@ class PatternShardedEngine:
             # [evaluations] log-likelihoods, [T x (2n-1)] edge derivatives and, with more than
             # one rate category, [T x (2n-1)] rate derivatives -- one collective.
             T, N = staged.tree_count, staged.node_count
-            if arrays_wanted > 1:
+            if substitution_sums:
+                count = lib.sbnb_batch_evaluation_count(staged._handle) + 2 * T * N + _capi.SUBSTITUTION_SUMS * T
+            elif arrays_wanted > 1:
                 count = lib.sbnb_batch_evaluation_count(staged._handle) + (2 if pointers[2].value else 1) * T * N
             else:
                 count = T
@@ -235,9 +272,12 @@ class PatternShardedEngine:
                 view = torch.as_tensor(_DeviceArrayView(pointers[0].value, count), device=f"cuda:{self.engine.device}")
                 _dist().all_reduce(view, op=_dist().ReduceOp.SUM)
             stream.synchronize()
-            return staged.fetch(gradients=arrays_wanted > 1)
+            result = staged.fetch(gradients=arrays_wanted > 1)
+            return (*result, staged.fetch_substitution_sums()) if substitution_sums else result
         result = staged.fetch(gradients=arrays_wanted > 1)
         arrays = list(result) if arrays_wanted > 1 else [result]
+        if substitution_sums:
+            arrays.append(staged.fetch_substitution_sums())
         all_reduce_sum_host(*arrays)
         return tuple(arrays) if arrays_wanted > 1 else arrays[0]
 
@@ -251,9 +291,17 @@ class PatternShardedEngine:
         return logl
 
     def gradients(self, trees, params=None, rescaling=False, rooted=False, substitution_gradient=True):
-        fd = substitution_gradient and self.specification.substitution in ("GTR", "HKY")
-        staged = self.engine.stage(trees, params, rooted=rooted, substitution_fd=fd)
+        wanted = substitution_gradient and self.specification.substitution in ("GTR", "HKY")
+        analytic = wanted and self.engine.substitution_gradient_mode == "analytic"
+        fd = wanted and not analytic
+        staged = self.engine.stage(trees, params, rooted=rooted, substitution_fd=fd, substitution_analytic=analytic)
         staged.run(_capi.MODE_BRANCH_GRADIENT, rescaling)
+        if analytic:
+            logl, grad, rgrad, sums = self._reduce(staged, 3, substitution_sums=True)
+            staged.close()
+            return finish_gradients_analytic(self.specification, self.engine.taxon_count, trees, rooted,
+                                             self.engine._params(params, trees.tree_count), logl, grad, rgrad, sums,
+                                             self.engine.category_count)
         logl, grad, rgrad = self._reduce(staged, 3)
         staged.close()
         return finish_gradients(self.specification, self.engine.taxon_count, trees, rooted, fd, logl, grad, rgrad,
@@ -261,4 +309,4 @@ class PatternShardedEngine:
 
 
 __all__ = ["TreeShardedEngine", "PatternShardedEngine", "shard_range", "pattern_range", "all_reduce_sum_host",
-           "all_gather_rows", "finish_gradients", "finish_log_likelihoods_rooted", "gather_gradients", "TreeBatch"]
+           "all_gather_rows", "finish_gradients", "finish_gradients_analytic", "finish_log_likelihoods_rooted", "gather_gradients", "TreeBatch"]

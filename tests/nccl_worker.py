@@ -37,6 +37,12 @@ def main():
         assert np.max(np.abs(logl - want["log_likelihood"]) / np.abs(want["log_likelihood"])) < 1e-10, cls
         assert np.max(np.abs(grad - want["branch"])) < 1e-8 * np.max(np.abs(want["branch"])), cls
         assert np.max(np.abs(site - want["site_model"])) < 1e-8 * np.max(np.abs(want["site_model"])), cls
+        # the full call: the substitution block analytically, its sums reduced with the rest
+        full = engine.gradients(batch, params, rescaling=True)
+        sub = np.array([g.gradient["substitution_model"] for g in full])
+        noise = np.abs(want["log_likelihood"]).max() * 1e-12 / 1e-6  # of the oracle's finite differences
+        assert np.max(np.abs(sub - want["substitution_model"])) < 2 * noise, cls
+        assert np.array_equal(np.array([g.gradient["branch_lengths"] for g in full]), grad), cls
         only_logl = engine.log_likelihoods(batch, params, rescaling=True)
         assert np.max(np.abs(only_logl - want["log_likelihood"]) / np.abs(want["log_likelihood"])) < 1e-10, cls
         # every rank holds the same bits (one collective, same reduction order everywhere)

@@ -43,6 +43,7 @@ def test_pattern_ranges_sum_to_the_whole_unrooted(world):
     spec = sbn.PhyloModelSpecification("GTR", "weibull+4", "none")
     engine = sbn.Engine(spec, states, weights, 0)
     batch = sbn.TreeBatch(parent_ids, lengths)
+    engine.set_substitution_gradient("fd")  # this test is about the finite-difference evaluations
     want = engine.gradients(batch, params, rescaling=True)
     ranges = [sharding.pattern_range(r, world, patterns) for r in range(world)]
     logl, grad, rgrad = raw_sums_over_ranges(engine, batch, params, ranges, False, True)
@@ -55,6 +56,35 @@ def test_pattern_ranges_sum_to_the_whole_unrooted(world):
     # relative reordering noise of the sums by 1e6 / 2
     a, b = stack(got, "substitution_model"), stack(want, "substitution_model")
     assert np.max(np.abs(a - b)) <= np.abs(logl).max() * 1e-12 / 1e-6
+
+
+@pytest.mark.parametrize("substitution", ["GTR", "HKY"])
+def test_analytic_substitution_sums_add_up_over_pattern_ranges(substitution):
+    """The 20 sums per tree of the analytic substitution gradient are sums over site
+    patterns like the other raw results: ranks add them and finish once."""
+    taxa, patterns, tree_count, world = 14, 4000, 6, 3
+    states, weights = trees.random_alignment(taxa, patterns, seed=3, gap_fraction=0.02)
+    parent_ids, lengths = trees.random_tree_batch(taxa, tree_count, seed=4)
+    row = GTR_ROW if substitution == "GTR" else [0.1, 0.2, 0.3, 0.4, 2.0, 0.5]
+    params = np.tile(np.array(row), (tree_count, 1))
+    spec = sbn.PhyloModelSpecification(substitution, "weibull+4", "none")
+    engine = sbn.Engine(spec, states, weights, 0)
+    batch = sbn.TreeBatch(parent_ids, lengths)
+    want = engine.gradients(batch, params, rescaling=True)
+    total = None
+    for rank in range(world):
+        engine.set_pattern_range(*sharding.pattern_range(rank, world, patterns))
+        staged = engine.stage(batch, params, substitution_analytic=True)
+        staged.run(_capi.MODE_BRANCH_GRADIENT, True)
+        parts = list(staged.fetch(gradients=True)) + [staged.fetch_substitution_sums()]
+        staged.close()
+        total = parts if total is None else [t + p for t, p in zip(total, parts)]
+    engine.set_pattern_range(0, patterns)
+    got = sharding.finish_gradients_analytic(spec, taxa, batch, False, params, *total, engine.category_count)
+    np.testing.assert_allclose([g.log_likelihood for g in got], [g.log_likelihood for g in want], rtol=1e-12)
+    for key in ("branch_lengths", "site_model", "substitution_model"):
+        a, b = stack(got, key), stack(want, key)
+        assert np.max(np.abs(a - b)) <= 1e-10 * np.max(np.abs(b)), key
 
 
 def test_pattern_ranges_sum_to_the_whole_rooted():
