@@ -4,6 +4,7 @@
 #define SBNB_DEVICE_COMMON_CUH_
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost nothing unless a profiler is attached
 
 #include <algorithm>
 #include <cfenv>
@@ -90,6 +91,14 @@ class PinnedArena {
   size_t capacity_ = 0, used_ = 0;
 };
 
+
+// NVTX range over a host-side phase (stage / run / fetch / finish), for nsys / ncu timelines.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Every C-ABI entry point runs inside Guard: exceptions become error codes, and
 // the caller's floating-point environment comes back exactly as it went in.  The

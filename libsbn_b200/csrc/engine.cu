@@ -120,6 +120,10 @@ struct sbnb_batch {
   bool slide_root = false;
   int fd_coords = 0;  // stick-breaking coordinates perturbed (0 if no FD staged)
   bool with_subst = false;  // staged for the analytic substitution gradient (Phi in the pre-order blocks)
+  bool rooted_finish = false;  // time-tree fields staged: gradient runs end with RootedFinishKernel
+  int rate_count = 0;
+  size_t children_at = 0, rooted_fields_at = 0;
+  DeviceArray<double> rooted_scratch;
   int vtree_count = 0;
   int slots = 1;
   int last_mode = -1;
@@ -132,7 +136,7 @@ struct sbnb_batch {
   // re-evaluates the same trees with new branch lengths, vip/burrito.py:84-117).
   std::vector<int32_t> cached_parent_ids;
   int cached_input_nodes = 0, cached_padded_categories = 0;
-  bool cached_with_subst = false;
+  bool cached_with_subst = false, cached_rooted_finish = false;
   // device side: one packed input buffer
   //   [lengths | models | vtree_program | vtree_model | vtree_lengths]   every call
   //   [ops | edge_offsets]                                              per topology set
@@ -171,6 +175,9 @@ struct sbnb_batch {
   double* ResultGrad() const { return results.get() + vtree_count; }
   double* ResultRateGrad() const { return ResultGrad() + static_cast<size_t>(tree_count) * node_count; }
   double* ResultSubst() const { return ResultRateGrad() + static_cast<size_t>(tree_count) * node_count; }
+  double* ResultRooted() const { return ResultSubst() + static_cast<size_t>(tree_count) * kOeSubstSums; }
+  // per tree: n-1 ratio / root-height entries, the clock gradient, the site-model gradient
+  size_t RootedWidth() const { return static_cast<size_t>(taxon_count - 1) + rate_count + 1; }
 };
 
 sbnb_engine::~sbnb_engine() {
@@ -542,6 +549,8 @@ void PackProgram(const TreeProgram& program, int n, int C, bool with_subst, OeOp
   Require(at / 2 < (int64_t{1} << 31), "Tree too large.");
 }
 
+RootedView ViewOf(const sbnb_tree_batch* trees, int t, int n);
+
 // Waits until the copy out of the staging arena that the previous Stage queued has
 // been done (normally long ago: every fetch synchronises the stream).
 void WaitForStaging(sbnb_engine* e) {
@@ -552,6 +561,7 @@ void WaitForStaging(sbnb_engine* e) {
 
 BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* params, bool rooted,
                bool with_fd, bool slide_root, bool with_subst = false) {
+  NvtxRange range("sbnb stage");
   CheckTrees(e, trees, rooted);
   const ModelSpec& spec = e->spec;
   Require(spec.param_count == 0 || params != nullptr || trees->tree_count == 0,
@@ -587,7 +597,14 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   };
   batch->ops_at = place(op_count * sizeof(OeOp));
   batch->edge_offsets_at = place(edge_count * sizeof(int2));
+  // Rooted time trees with all their fields: the O(n) gradient finishing runs on the device.
+  batch->rooted_finish = rooted && trees->node_heights && trees->node_bounds && trees->height_ratios &&
+                         (trees->rate_count == 1 || trees->rate_count == N - 1);
+  batch->rate_count = batch->rooted_finish ? trees->rate_count : 0;
+  batch->children_at = place(batch->rooted_finish ? static_cast<size_t>(T) * 2 * N * sizeof(int32_t) : 0);
   const size_t per_call_begin = at;
+  const size_t rooted_stride = 4 * static_cast<size_t>(N) + n - 2;  // doubles per tree
+  batch->rooted_fields_at = place(batch->rooted_finish ? static_cast<size_t>(T) * rooted_stride * sizeof(double) : 0);
   batch->lengths_at = place(static_cast<size_t>(T) * N * sizeof(double));
   batch->models_at = place(max_models * sizeof(ModelTables));
   batch->vtree_program_at = place(batch->vtree_count * sizeof(int32_t));
@@ -599,6 +616,7 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   const size_t id_count = static_cast<size_t>(T) * (trees->node_count - 1);
   const bool cached = same_shape && batch->cached_input_nodes == trees->node_count &&
                       batch->cached_padded_categories == C && batch->cached_with_subst == with_subst &&
+                      batch->cached_rooted_finish == batch->rooted_finish &&
                       batch->cached_parent_ids.size() == id_count &&
                       batch->input.capacity() >= total_bytes &&
                       std::memcmp(batch->cached_parent_ids.data(), trees->parent_ids, id_count * sizeof(int32_t)) == 0;
@@ -644,6 +662,27 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
     batch->cached_input_nodes = trees->node_count;
     batch->cached_padded_categories = C;
     batch->cached_with_subst = with_subst;
+    batch->cached_rooted_finish = batch->rooted_finish;
+    if (batch->rooted_finish) {
+      int32_t* children = reinterpret_cast<int32_t*>(host + batch->children_at);
+      for (int t = 0; t < T; t++) {
+        std::copy(batch->programs[t].child0.begin(), batch->programs[t].child0.end(), children + static_cast<size_t>(t) * 2 * N);
+        std::copy(batch->programs[t].child1.begin(), batch->programs[t].child1.end(),
+                  children + static_cast<size_t>(t) * 2 * N + N);
+      }
+    }
+  }
+  if (batch->rooted_finish) {
+    double* fields = reinterpret_cast<double*>(host + batch->rooted_fields_at);
+    for (int t = 0; t < T; t++) {
+      double* row = fields + static_cast<size_t>(t) * rooted_stride;
+      const RootedView view = ViewOf(trees, t, n);
+      row = std::copy(view.rates, view.rates + (N - 1), row);
+      row = std::copy(view.branch_lengths, view.branch_lengths + N, row);
+      row = std::copy(view.node_heights, view.node_heights + N, row);
+      row = std::copy(view.node_bounds, view.node_bounds + N, row);
+      std::copy(view.height_ratios, view.height_ratios + (n - 1), row);
+    }
   }
   for (int t = 0; t < T; t++)
     EffectiveBranchLengths(batch->programs[t], trees, t, rooted, batch->slide_root, N,
@@ -688,7 +727,9 @@ BatchPtr Stage(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   SBNB_CUDA(cudaEventRecord(e->staging_free, s));
   e->staging_in_flight = true;
   e->h2d_bytes += copy_bytes;
-  batch->results.Reserve(batch->vtree_count + 2 * static_cast<size_t>(T) * N + static_cast<size_t>(T) * kOeSubstSums);
+  batch->results.Reserve(batch->vtree_count + 2 * static_cast<size_t>(T) * N + static_cast<size_t>(T) * kOeSubstSums +
+                         (batch->rooted_finish ? static_cast<size_t>(T) * batch->RootedWidth() : 0));
+  if (batch->rooted_finish) batch->rooted_scratch.Reserve(static_cast<size_t>(T) * 5 * (n - 1));
   return batch;
 }
 
@@ -751,6 +792,7 @@ void LaunchMatrices(sbnb_engine* e, sbnb_batch* b, double* operands, int64_t str
 }
 
 void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling, bool timed = true) {
+  NvtxRange range("sbnb run");
   Require(mode == SBNB_MODE_LOG_LIKELIHOOD || mode == SBNB_MODE_BRANCH_GRADIENT, "Unknown mode.");
   SBNB_CUDA(cudaSetDevice(e->device));
   b->last_mode = mode;
@@ -846,21 +888,41 @@ void Run(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling, bool timed = t
     SBNB_CUDA(cudaGetLastError());
     e->launch_count++;
   }
+  if (grad && b->rooted_finish) {
+    RootedFinishParams r{};
+    r.tree_count = T;
+    r.taxon_count = b->taxon_count;
+    r.rate_count = b->rate_count;
+    r.children = b->At<int32_t>(b->children_at);
+    r.fields = b->At<double>(b->rooted_fields_at);
+    r.scaled_lengths = b->At<double>(b->lengths_at);
+    r.grad = b->ResultGrad();
+    r.rgrad = C > 1 ? b->ResultRateGrad() : nullptr;
+    r.scratch = b->rooted_scratch.get();
+    r.out = b->ResultRooted();
+    const int block = 64;
+    RootedFinishKernel<<<(T + block - 1) / block, block, 0, s>>>(r);
+    SBNB_CUDA(cudaGetLastError());
+    e->launch_count++;
+  }
 }
 
 // How many doubles of the result array a fetch of these outputs copies.
-size_t FetchCount(const sbnb_engine* e, const sbnb_batch* b, bool grad, bool rgrad, bool subst) {
+size_t FetchCount(const sbnb_engine* e, const sbnb_batch* b, bool grad, bool rgrad, bool subst,
+                  bool rooted = false) {
   const bool was_grad = (b->last_mode == SBNB_MODE_BRANCH_GRADIENT);
   const size_t vtrees = was_grad ? b->vtree_count : b->tree_count;
   const size_t grad_count = static_cast<size_t>(b->tree_count) * b->node_count;
   const bool rates = rgrad && e->padded_categories > 1;
+  if (rooted)
+    return b->vtree_count + 2 * grad_count + static_cast<size_t>(b->tree_count) * (kOeSubstSums + b->RootedWidth());
   if (subst) return b->vtree_count + 2 * grad_count + static_cast<size_t>(b->tree_count) * kOeSubstSums;
   return (grad || rates) ? b->vtree_count + (rates ? 2 : 1) * grad_count : vtrees;
 }
 
 // Results that have landed in page-locked memory -> the caller's arrays.
 void Unpack(const sbnb_engine* e, const sbnb_batch* b, const double* landed, double* logl, double* grad,
-            double* rgrad, double* subst) {
+            double* rgrad, double* subst, double* rooted = nullptr) {
   const bool was_grad = (b->last_mode == SBNB_MODE_BRANCH_GRADIENT);
   const size_t vtrees = was_grad ? b->vtree_count : b->tree_count;
   const size_t grad_count = static_cast<size_t>(b->tree_count) * b->node_count;
@@ -873,12 +935,17 @@ void Unpack(const sbnb_engine* e, const sbnb_batch* b, const double* landed, dou
       std::fill(rgrad, rgrad + grad_count, 0.0);
     }
   }
-  if (subst)
-    std::copy(landed + b->vtree_count + 2 * grad_count,
-              landed + b->vtree_count + 2 * grad_count + static_cast<size_t>(b->tree_count) * kOeSubstSums, subst);
+  const size_t subst_count = static_cast<size_t>(b->tree_count) * kOeSubstSums;
+  if (subst) std::copy(landed + b->vtree_count + 2 * grad_count, landed + b->vtree_count + 2 * grad_count + subst_count, subst);
+  if (rooted) {
+    const double* from = landed + b->vtree_count + 2 * grad_count + subst_count;
+    std::copy(from, from + static_cast<size_t>(b->tree_count) * b->RootedWidth(), rooted);
+  }
 }
 
-void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rgrad, double* subst = nullptr) {
+void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rgrad, double* subst = nullptr,
+           double* rooted = nullptr) {
+  NvtxRange range("sbnb fetch");
   SBNB_CUDA(cudaSetDevice(e->device));
   Require(b->last_mode >= 0, "sbnb_batch_fetch called before sbnb_batch_run.");
   const bool was_grad = (b->last_mode == SBNB_MODE_BRANCH_GRADIENT);
@@ -890,13 +957,14 @@ void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rg
     return;
   }
   // One copy of what is asked for into page-locked memory, then out to the caller's arrays.
-  const size_t count = FetchCount(e, b, grad != nullptr, rgrad != nullptr, subst != nullptr);
+  if (rooted) Require(was_grad && b->rooted_finish, "No finished rooted gradients: the batch carries no time-tree fields.");
+  const size_t count = FetchCount(e, b, grad != nullptr, rgrad != nullptr, subst != nullptr, rooted != nullptr);
   e->landing.Reset(count * sizeof(double));
   double* landed = e->landing.Take<double>(count);
   SBNB_CUDA(cudaMemcpyAsync(landed, b->results.get(), count * sizeof(double), cudaMemcpyDeviceToHost, s));
   e->d2h_bytes += count * sizeof(double);
   SBNB_CUDA(cudaStreamSynchronize(s));
-  Unpack(e, b, landed, logl, grad, rgrad, subst);
+  Unpack(e, b, landed, logl, grad, rgrad, subst, rooted);
 }
 
 // Run + Fetch of the one-call entry points.  Once the same topology set has come in
@@ -905,19 +973,19 @@ void Fetch(sbnb_engine* e, sbnb_batch* b, double* logl, double* grad, double* rg
 // 4-6 launches, 2 event records and a copy (the small-problem regime of
 // BASELINE.json configs[0..1], where a call is tens of microseconds).
 void RunAndFetch(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling, double* logl, double* grad,
-                 double* rgrad, double* subst = nullptr) {
+                 double* rgrad, double* subst = nullptr, double* rooted = nullptr) {
   static const bool graphs_enabled = EnvInt("SBNB_GRAPHS", 1) != 0;
   sbnb_batch::Graph& graph = b->graphs[mode == SBNB_MODE_BRANCH_GRADIENT ? 1 : 0][rescaling ? 1 : 0];
   if (!graphs_enabled || b->tree_count == 0 || b->cache_hits < 1 || !graph.warm) {
     Run(e, b, mode, rescaling);
-    Fetch(e, b, logl, grad, rgrad, subst);
+    Fetch(e, b, logl, grad, rgrad, subst, rooted);
     graph.warm = b->cache_hits >= 1;  // (an eager run on cached programs: the next one may be captured)
     return;
   }
   SBNB_CUDA(cudaSetDevice(e->device));
   cudaStream_t s = e->stream;
   b->last_mode = mode;
-  const size_t count = FetchCount(e, b, grad != nullptr, rgrad != nullptr, subst != nullptr);
+  const size_t count = FetchCount(e, b, grad != nullptr, rgrad != nullptr, subst != nullptr, rooted != nullptr);
   e->landing.Reset(count * sizeof(double));
   double* landed = e->landing.Take<double>(count);
   auto signature = [&] {
@@ -931,7 +999,7 @@ void RunAndFetch(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling, double
         reinterpret_cast<uintptr_t>(e->weights.get()),      reinterpret_cast<uintptr_t>(landed),
         static_cast<uintptr_t>(count),                      static_cast<uintptr_t>(b->vtree_count),
         static_cast<uintptr_t>(b->with_subst),              static_cast<uintptr_t>(e->range_end - e->range_begin),
-        static_cast<uintptr_t>(b->slots)};
+        static_cast<uintptr_t>(b->slots),                   reinterpret_cast<uintptr_t>(b->rooted_scratch.get())};
   };
   if (graph.exec == nullptr || graph.signature != signature()) {
     if (graph.exec) {
@@ -963,7 +1031,7 @@ void RunAndFetch(sbnb_engine* e, sbnb_batch* b, int mode, bool rescaling, double
   e->launch_count += graph.kernels;
   e->d2h_bytes += count * sizeof(double);
   SBNB_CUDA(cudaStreamSynchronize(s));
-  Unpack(e, b, landed, logl, grad, rgrad, subst);
+  Unpack(e, b, landed, logl, grad, rgrad, subst, rooted);
 }
 
 RootedView ViewOf(const sbnb_tree_batch* trees, int t, int n) {
@@ -1055,7 +1123,9 @@ void LogLikelihoods(sbnb_engine* e, const sbnb_tree_batch* trees, const double* 
 void FinishGradients(const ModelSpec& spec, int n, const sbnb_tree_batch* trees, bool rooted, int fd_coords,
                      const double* logl, const double* grad, const double* rgrad,
                      const sbnb_gradient_out* out, const std::vector<TreeProgram>* programs = nullptr,
-                     const double* params = nullptr, const double* subst_sums = nullptr) {
+                     const double* params = nullptr, const double* subst_sums = nullptr,
+                     const double* rooted_finished = nullptr, size_t rooted_width = 0) {
+  NvtxRange range("sbnb finish gradients");
   Require(trees != nullptr, "NULL tree batch.");
   Require(out != nullptr, "NULL gradient output.");
   const int T = trees->tree_count, N = 2 * n - 1;
@@ -1094,6 +1164,16 @@ void FinishGradients(const ModelSpec& spec, int n, const sbnb_tree_batch* trees,
         out->substitution_model[static_cast<size_t>(t) * derivatives.count + k] = value;
       }
     }
+    if (rooted && rooted_finished != nullptr) {
+      // RootedFinishKernel has done the O(n) tail on the device: [ratios | clock | site model]
+      const double* row = rooted_finished + static_cast<size_t>(t) * rooted_width;
+      if (out->ratios_root_height) std::copy(row, row + (n - 1), out->ratios_root_height + static_cast<size_t>(t) * (n - 1));
+      if (out->clock_model)
+        std::copy(row + (n - 1), row + (n - 1) + trees->rate_count,
+                  out->clock_model + static_cast<size_t>(t) * trees->rate_count);
+      if (out->site_model && categories > 1) out->site_model[t] = row[rooted_width - 1];
+      return;
+    }
     if (out->site_model && categories > 1) {
       EffectiveBranchLengths(tree, trees, t, rooted, /*slide_root=*/true, N, lengths.data());
       out->site_model[t] =
@@ -1126,12 +1206,15 @@ void Gradients(sbnb_engine* e, const sbnb_tree_batch* trees, const double* param
   const bool analytic = wanted && e->substitution_mode == SBNB_SUBSTITUTION_ANALYTIC;
   auto batch = Stage(e, trees, params, rooted, wanted && !analytic, /*slide_root=*/true, analytic);
   const int T = trees->tree_count, N = 2 * e->taxon_count - 1;
+  const bool finished_on_device = batch->rooted_finish && T > 0;
   std::vector<double> logl(batch->vtree_count), grad(static_cast<size_t>(T) * N),
-      rgrad(static_cast<size_t>(T) * N), subst(analytic ? static_cast<size_t>(T) * kOeSubstSums : 0);
+      rgrad(static_cast<size_t>(T) * N), subst((analytic || finished_on_device) ? static_cast<size_t>(T) * kOeSubstSums : 0),
+      finished(finished_on_device ? static_cast<size_t>(T) * batch->RootedWidth() : 0);
   RunAndFetch(e, batch.get(), SBNB_MODE_BRANCH_GRADIENT, rescaling, logl.data(), grad.data(), rgrad.data(),
-              analytic && T > 0 ? subst.data() : nullptr);
+              analytic && T > 0 ? subst.data() : nullptr, finished_on_device ? finished.data() : nullptr);
   FinishGradients(e->spec, e->taxon_count, trees, rooted, batch->fd_coords, logl.data(), grad.data(),
-                  rgrad.data(), out, &batch->programs, params, analytic && T > 0 ? subst.data() : nullptr);
+                  rgrad.data(), out, &batch->programs, params, analytic && T > 0 ? subst.data() : nullptr,
+                  finished_on_device ? finished.data() : nullptr, finished_on_device ? batch->RootedWidth() : 0);
 }
 
 

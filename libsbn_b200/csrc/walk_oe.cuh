@@ -298,6 +298,109 @@ __global__ void ReduceAllKernel(const double* __restrict__ logl_partial, const d
   dst[k] = sum;
 }
 
+// Rooted time trees: the O(n) tail of FatBeagle::Gradient(RootedTree) (fat_beagle.cpp:505-545)
+// behind the reduction, one thread per tree -- RatioGradientOfBranchGradient
+// (rooted_gradient_transforms.cpp:17-170: height gradient, chain rule to the height ratios
+// through the epoch structure, root height, gradient of the log-det-Jacobian), ClockGradient
+// and DiscreteSiteModelGradient (fat_beagle.cpp:367-398) -- so a rooted gradient leaves the
+// device finished.  Internal node ids ascend in post-order, so an ascending loop is a
+// post-order pass and a descending loop a pre-order pass (the same arithmetic as
+// csrc/rooted.cpp, which finishes sharded runs on the host).
+struct RootedFinishParams {
+  int32_t tree_count, taxon_count, rate_count;
+  const int32_t* children;   // [tree][2][2n-1]: child0 then child1 per node id (-1 for leaves)
+  const double* fields;      // [tree]: rates (2n-2), branch lengths (2n-1), heights (2n-1), bounds (2n-1), ratios (n-1)
+  const double* scaled_lengths;  // [tree][2n-1] branch length x rate, what the walk used
+  const double* grad;        // [tree][2n-1] edge derivatives
+  const double* rgrad;       // [tree][2n-1] or NULL (one category)
+  double* scratch;           // [tree][5][n-1]
+  double* out;               // [tree][(n-1) + rate_count + 1]: ratios / root height, clock, site model
+};
+
+__global__ void RootedFinishKernel(const RootedFinishParams p) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.tree_count) return;
+  const int n = p.taxon_count, N = 2 * n - 1, root = N - 1;
+  const int32_t* child0 = p.children + static_cast<size_t>(t) * 2 * N;
+  const int32_t* child1 = child0 + N;
+  const double* rates = p.fields + static_cast<size_t>(t) * (4 * N + n - 2);
+  const double* lengths = rates + (N - 1);
+  const double* heights = lengths + N;
+  const double* bounds = heights + N;
+  const double* ratios = bounds + N;
+  const double* g = p.grad + static_cast<size_t>(t) * N;
+  double* height_gradient = p.scratch + static_cast<size_t>(t) * 5 * (n - 1);
+  double* chain = height_gradient + (n - 1);
+  double* log_time = chain + (n - 1);
+  double* jacobian = log_time + (n - 1);
+  double* multiplier = jacobian + (n - 1);
+  double* out = p.out + static_cast<size_t>(t) * (n - 1 + p.rate_count + 1);
+
+  auto node_partial = [&](int node) { return (heights[node] - bounds[node]) / ratios[node - n]; };
+  auto epoch_addition = [&](int node, int child, const double* ratio_gradient) {
+    if (child < n) return 0.0;
+    if (bounds[node] == bounds[child]) return ratio_gradient[child - n] * ratios[child - n] / ratios[node - n];
+    return ratio_gradient[child - n] * ratios[child - n] / (heights[node] - bounds[child]) * node_partial(node);
+  };
+  auto ratio_chain = [&](const double* height_terms, double* result) {
+    for (int node = n; node < N; node++) {
+      if (node == root) {
+        result[node - n] = 0.0;
+        continue;
+      }
+      double value = node_partial(node) * height_terms[node - n];
+      result[node - n] = value;  // (the children's entries are complete: ids ascend in post-order)
+      value += epoch_addition(node, child0[node], result);
+      result[node - n] = value;
+      value += epoch_addition(node, child1[node], result);
+      result[node - n] = value;
+    }
+  };
+  auto root_height_chain = [&](const double* terms) {
+    for (int i = 0; i < n - 1; i++) multiplier[i] = 0.0;
+    multiplier[root - n] = 1.0;
+    for (int node = N - 1; node >= n; node--) {
+      const int c0 = child0[node], c1 = child1[node];
+      if (c0 >= n) multiplier[c0 - n] = ratios[c0 - n] * multiplier[node - n];
+      if (c1 >= n) multiplier[c1 - n] = ratios[c1 - n] * multiplier[node - n];
+    }
+    double sum = 0.0;
+    for (int i = 0; i < n - 1; i++) sum += terms[i] * multiplier[i];
+    return sum;
+  };
+
+  for (int node = n; node < N; node++) {
+    double value = 0.0;
+    if (node != root) value = -g[node] * rates[node];
+    value += g[child0[node]] * rates[child0[node]];
+    value += g[child1[node]] * rates[child1[node]];
+    height_gradient[node - n] = value;
+  }
+  ratio_chain(height_gradient, chain);
+  chain[root - n] = root_height_chain(height_gradient);
+  for (int i = 0; i < n - 1; i++) log_time[i] = (i < n - 2) ? 1.0 / (heights[n + i] - bounds[n + i]) : 0.0;
+  ratio_chain(log_time, jacobian);
+  jacobian[root - n] = root_height_chain(log_time);
+  for (int i = 0; i < n - 2; i++) out[i] = chain[i] + (jacobian[i] - 1.0 / ratios[i]);
+  out[root - n] = chain[root - n] + jacobian[root - n];
+
+  double* clock = out + (n - 1);
+  if (p.rate_count == 1) {
+    double sum = 0.0;
+    for (int i = 0; i < N - 1; i++) sum += g[i] * lengths[i];
+    clock[0] = sum;
+  } else {
+    for (int i = 0; i < N - 1; i++) clock[i] = g[i] * lengths[i];
+  }
+  double site = 0.0;
+  if (p.rgrad != nullptr) {
+    const double* rg = p.rgrad + static_cast<size_t>(t) * N;
+    const double* scaled = p.scaled_lengths + static_cast<size_t>(t) * N;
+    for (int node = 0; node < N - 1; node++) site += rg[node] * scaled[node];
+  }
+  out[n - 1 + p.rate_count] = site;
+}
+
 // Device groups sharded by site pattern (engine.cu): the raw per-tree sums of the other
 // devices, read through peer pointers over NVLink, are added onto this device's array.
 struct PeerPointers {
