@@ -70,9 +70,36 @@ int sbnb_gp_create(int32_t taxon_count, int64_t pattern_count, const uint8_t* ti
                    const double* inverted_sbn_prior, int32_t device, sbnb_gp_engine** out);
 void sbnb_gp_destroy(sbnb_gp_engine* engine);
 
+/*
+ * The substitution model behind every transition matrix and the stationary distribution.
+ * The reference's GPEngine is hard-wired to JC69 (gp_engine.hpp:143-154); this
+ * is an addition.  `substitution` and `params` as in the "entire substitution" block of a
+ * phylo_model_params row (sbn_b200.h): "JC69" (no parameters, the default), "GTR" (6 rates,
+ * then 4 frequencies; substitution_model.cpp:39-80) or "HKY" (4 frequencies, then kappa:
+ * sub-blocks in key order, block_specification.cpp:10-21).
+ * Takes effect with the next call; PLVs computed before are not touched.
+ */
+int sbnb_gp_set_substitution_model(sbnb_gp_engine* engine, const char* substitution, const double* params,
+                                   int32_t param_count);
+
 /* GPEngine::ProcessOperations (gp_engine.cpp:167-171): the whole program in one
  * kernel launch; returns after it has finished. */
 int sbnb_gp_process_operations(sbnb_gp_engine* engine, const int32_t* program, int64_t word_count);
+
+/*
+ * The schedule the device runs for `program` (host only, no device needed; what
+ * sbnb_gp_process_operations does first): the same records re-ordered by dependency level --
+ * an op's level is one more than the highest level of the ops it must follow (read after
+ * write, write after write, write after read over PLVs, rescaling counts, q, branch lengths,
+ * log-likelihood rows, the log-marginal vector) -- and inside a level by kind, so that every
+ * value is computed by the same arithmetic as in the reference's sequential order
+ * (GPEngine::ProcessOperations, gp_engine.cpp:167-171).  Word 0 of the first record of a run of
+ * mutually independent records of one kind carries the run length in bits 8 and up (the
+ * interpreter issues their loads together); the opcode is word 0 & 0xff.  out receives
+ * word_count words.
+ */
+int sbnb_gp_schedule_program(int32_t plv_count, int32_t gpcsp_count, const int32_t* program,
+                             int64_t word_count, int32_t* out);
 
 /* gp_engine.cpp:193-209. */
 int sbnb_gp_set_branch_lengths(sbnb_gp_engine* engine, const double* branch_lengths);

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cfenv>
+#include <cstdlib>
 #include <new>
 #include <string>
 
@@ -91,6 +92,12 @@ class PinnedArena {
   size_t capacity_ = 0, used_ = 0;
 };
 
+
+// Integer tuning knob from the environment (development aid).
+inline int EnvInt(const char* name, int fallback) {
+  const char* value = std::getenv(name);
+  return value ? std::atoi(value) : fallback;
+}
 
 // NVTX range over a host-side phase (stage / run / fetch / finish), for nsys / ncu timelines.
 struct NvtxRange {

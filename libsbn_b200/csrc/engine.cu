@@ -43,11 +43,6 @@ int PadCategories(int c) {
   return 0;
 }
 
-int EnvInt(const char* name, int fallback) {
-  const char* value = std::getenv(name);
-  return value ? std::atoi(value) : fallback;
-}
-
 }  // namespace
 
 void SetLastError(const std::string& message) { g_last_error = message; }

@@ -3,24 +3,34 @@
 // include/sbn_b200_gp.h.
 //
 // Design.  Every GP operation except three acts on site patterns independently,
-// so a thread owns a fixed set of patterns for the WHOLE program: one persistent
-// kernel interprets the op stream, and all data hazards between ops (op i + 1
-// reads the PLV op i wrote) are same-thread hazards that need no barrier.  The
-// PLVs stay in HBM/L2 ([plv][pattern][state], the reference's memory order,
-// mmapped_plv.hpp:15-41), 32 bytes per (PLV, pattern), one coalesced 32-byte
-// access per lane.  The three cross-pattern couplings are reductions:
+// so a thread owns one site pattern for the WHOLE program: one persistent kernel
+// interprets the op stream, and all data hazards between ops (op i + 1 reads the PLV
+// op i wrote) are same-thread hazards that need no barrier.  The PLVs stay in HBM/L2
+// ([plv][pattern][state], the reference's memory order, mmapped_plv.hpp:15-41), 32
+// bytes per (PLV, pattern).  The three cross-pattern couplings are reductions:
 //   * Multiply's finite check, min/max scan and conditional rescale
-//     (gp_engine.cpp:111-117, 288-320) -- one (max, min, flag) reduction per op
+//     (gp_engine.cpp:111-117, 288-320) -- one reduction of two integer keys per op
 //     instead of the reference's three full passes;
 //   * OptimizeBranchLength's objective (gp_engine.cpp:326-345): Brent's control
 //     flow runs redundantly in every thread on identical, deterministically
 //     reduced objective values, so no host round trip happens inside the search;
 //   * UpdateSBNProbabilities' per-GPCSP weighted sums (gp_engine.cpp:136-153).
-// Scalars (rescaling counts, branch lengths, q) are written redundantly by every
-// thread with identical values, so they need no barrier either.
-// One CTA (barrier = __syncthreads) serves up to 2048 patterns -- every DAG the
-// reference's tests use; beyond that a cooperative grid with one grid-wide
-// barrier per reduction.
+// Scalars (rescaling counts, branch lengths, q, the transition matrices of all
+// GPCSPs) live in shared memory and are written redundantly with identical values.
+//
+// At DS1 size an op is a chain of latencies, not arithmetic or bandwidth (measured: 0.13
+// instructions per cycle per warp, fixed-latency and scoreboard stalls), so the work is
+// arranged to shorten that chain:
+//   * the patterns are spread over several CTAs on different SMs (934 patterns: 8 CTAs of
+//     128 threads), which share nothing but the reductions -- exchanged through an
+//     LL-style mailbox in L2 (8-byte words carrying their own epoch flag: one round
+//     trip, no grid-wide barrier);
+//   * P(t) of every GPCSP is computed once per launch by half-warps and kept current by
+//     OptimizeBranchLength (every thread evaluating V exp(Lambda t) V^-1 for itself was
+//     ~290 fp64 instructions per op);
+//   * the host re-orders the program by dependency level (CompileProgram) and marks runs
+//     of independent ops of one kind as batches, whose loads are in flight together and
+//     whose reductions share one exchange.
 //
 // There is no CPU path in this file.
 
@@ -40,15 +50,17 @@
 
 namespace cg = cooperative_groups;
 
-constexpr int kGpProgramSmemWords = 8192;
 
 namespace sbnb {
 
 namespace {
 
-constexpr int kGpMaxBlockThreads = 512;
-constexpr int kGpSingleBlockPatterns = 2048;  // up to 4 patterns per thread in one CTA
-constexpr int kGpGridBlockThreads = 256;
+constexpr int kGpMaxBlockThreads = 256;
+constexpr int kGpBlockThreads = 128;      // one pattern per thread ...
+constexpr int kGpGridBlockThreads = 256;  // ... until the resident CTAs cannot hold them all
+constexpr size_t kGpSmemBudget = 200 * 1024;  // dynamic shared memory of the interpreter
+constexpr int kGpScratchDoubles = 256;
+constexpr size_t kGpProgramCacheSize = 16;
 
 // Status word written by the interpreter when a reference Assert would fire.
 enum GpFault : int {
@@ -57,7 +69,8 @@ enum GpFault : int {
   kGpFaultRescaledStationary = 2,  // gp_engine.cpp:89-90
   kGpFaultNotFinite = 3,         // gp_engine.cpp:115
   kGpFaultNegative = 4,          // gp_engine.cpp:300-301
-  kGpFaultBadProgram = 5
+  kGpFaultBadProgram = 5,
+  kGpFaultBarrierTimeout = 6  // a CTA of a multi-block launch never posted its partial results
 };
 
 struct GpParams {
@@ -74,8 +87,9 @@ struct GpParams {
   const int32_t* program;
   int64_t word_count;
   double threshold, log_threshold;
-  double* exchange;  // [2][blocks][4] cross-block reduction mailboxes
+  double* exchange;  // [2][blocks][2 kGpReduceValues] 8-byte words: cross-block reduction mailboxes
   int32_t* status;   // [2] = fault code, op index
+  double* matrix_cache;  // [gpcsp][16]: where the interpreter keeps P(t_g) when shared memory cannot
   double evec[16], ivec[16], eval[4], freqs[4];
 };
 
@@ -144,88 +158,227 @@ __device__ __forceinline__ double LogAdd(double x, double y) {
 
 // Deterministic reductions over every thread of the launch.  Each returns the
 // same bits in every thread.
+//   Inside a CTA: one barrier per reduction; the per-warp mailboxes are double-buffered --
+// a warp that writes buffer b for reduction r + 2 has passed the barrier of reduction r + 1,
+// which every warp reaches only after it has read buffer b in reduction r.
+//   Across CTAs (all co-resident: cooperative launch): no grid-wide barrier.  Every CTA posts
+// its partial results as 8-byte words {epoch : 32 | half of a double : 32} -- a 64-bit store
+// is single-copy atomic, so a word that shows the epoch carries its data (the LL protocol of
+// collective libraries) -- and polls the words of all CTAs: ONE L2 round trip after the last
+// CTA has posted, against several microseconds of a cooperative-groups grid sync.  The
+// mailboxes alternate with the epoch's parity: a CTA can post epoch r + 2 only after every
+// CTA has posted r + 1, i.e. after every CTA has read r.
+constexpr int kGpMaxGridBlocks = 160;
+#ifndef SBNB_GP_BATCH_OPS
+#define SBNB_GP_BATCH_OPS 2
+#endif
+constexpr int kGpBatch = SBNB_GP_BATCH_OPS;                        // ops of one batch whose loads are in flight together
+constexpr int kGpReduceValues = 2 * kGpBatch;      // values one reduction carries
+constexpr int kGpSpinLimit = 1 << 21;  // polls before a CTA gives up (a lost peer must not hang the device)
+
+// Order-preserving map of a double onto an unsigned 64-bit key (negative values below
+// positive ones, -0 just below +0, +inf and NaNs with a clear sign bit on top): maxima over
+// site patterns are taken on keys with integer compares and the warp-wide REDUX
+// instruction instead of a chain of NaN-aware fmax sequences.
+__device__ __forceinline__ unsigned long long SortableKey(double x) {
+  const long long bits = __double_as_longlong(x);
+  return static_cast<unsigned long long>(bits ^ ((bits >> 63) | static_cast<long long>(0x8000000000000000ull)));
+}
+__device__ __forceinline__ double FromSortableKey(unsigned long long key) {
+  const long long bits = static_cast<long long>(key);
+  return __longlong_as_double(bits < 0 ? (bits & 0x7fffffffffffffffll) : ~bits);
+}
+
 struct Reducer {
   const GpParams& p;
   bool multi_block;
-  int round = 0;  // alternates the cross-block mailbox
-  double (*smem)[4];
+  unsigned long long (*smem)[kGpMaxBlockThreads / 32][kGpReduceValues];  // [2][warp][value]
+  unsigned long long (*landed)[kGpReduceValues];  // [block][value] values of the other CTAs as they arrive
+  int* abort_flag;        // shared: a poll timed out
+  uint32_t epoch = 0;
+  int block_round = 0;    // alternates the per-warp mailboxes
+  bool dead = false;
 
-  // values[0..count): count <= 4 quantities reduced together; is_max[i] selects
-  // max instead of sum.
-  template <int COUNT>
-  __device__ void All(double (&values)[COUNT], const bool (&is_max)[COUNT]) {
+  // bits[0..COUNT): doubles that are summed (KEYS = false) or unsigned keys whose maximum is
+  // taken (KEYS = true), over every thread of the launch, in a fixed order.
+  template <int COUNT, bool KEYS>
+  __device__ void Exchange(unsigned long long (&bits)[COUNT]) {
+    static_assert(COUNT <= kGpReduceValues, "more values than a mailbox slot holds");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = (blockDim.x + 31) >> 5;
+    auto combine = [](unsigned long long a, unsigned long long b) -> unsigned long long {
+      if (KEYS) return a > b ? a : b;
+      return static_cast<unsigned long long>(
+          __double_as_longlong(__longlong_as_double(static_cast<long long>(a)) + __longlong_as_double(static_cast<long long>(b))));
+    };
 #pragma unroll
     for (int i = 0; i < COUNT; i++) {
+      if (KEYS) {
+        const unsigned hi = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(bits[i] >> 32));
+        const unsigned lo = __reduce_max_sync(
+            0xffffffffu, static_cast<unsigned>(bits[i] >> 32) == hi ? static_cast<unsigned>(bits[i]) : 0u);
+        bits[i] = (static_cast<unsigned long long>(hi) << 32) | lo;
+      } else {
 #pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) {
-        const double other = __shfl_xor_sync(0xffffffffu, values[i], m);
-        values[i] = is_max[i] ? fmax(values[i], other) : values[i] + other;
+        for (int m = 16; m >= 1; m >>= 1) bits[i] = combine(bits[i], __shfl_xor_sync(0xffffffffu, bits[i], m));
       }
     }
-    __syncthreads();  // the previous reduction's readers are done with smem
+    unsigned long long(*box)[kGpReduceValues] = smem[block_round & 1];
+    block_round++;
     if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < COUNT; i++) smem[warp][i] = values[i];
+      for (int i = 0; i < COUNT; i++) box[warp][i] = bits[i];
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < COUNT; i++) {
-      double total = smem[0][i];
-      for (int w = 1; w < warps; w++) total = is_max[i] ? fmax(total, smem[w][i]) : total + smem[w][i];
-      values[i] = total;
+      unsigned long long total = box[0][i];
+      for (int w = 1; w < warps; w++) total = combine(total, box[w][i]);
+      bits[i] = total;
     }
-    if (multi_block) {
-      double* mailbox = p.exchange + static_cast<size_t>(round & 1) * gridDim.x * 4;
-      round++;
-      if (threadIdx.x == 0) {
+    if (multi_block && !dead) {
+      epoch++;
+      unsigned long long* const mailbox = reinterpret_cast<unsigned long long*>(p.exchange) +
+                                          static_cast<size_t>(epoch & 1) * gridDim.x * (2 * kGpReduceValues);
+      if (threadIdx.x < 2 * COUNT) {
+        unsigned long long mine = bits[0];
 #pragma unroll
-        for (int i = 0; i < COUNT; i++) mailbox[blockIdx.x * 4 + i] = values[i];
+        for (int i = 1; i < COUNT; i++) mine = (static_cast<int>(threadIdx.x >> 1) == i) ? bits[i] : mine;
+        const unsigned half = (threadIdx.x & 1) ? static_cast<unsigned>(mine >> 32) : static_cast<unsigned>(mine);
+        *reinterpret_cast<volatile unsigned long long*>(mailbox + blockIdx.x * (2 * kGpReduceValues) + threadIdx.x) =
+            (static_cast<unsigned long long>(epoch) << 32) | half;
       }
-      __threadfence();
-      cg::this_grid().sync();
+      const int words = static_cast<int>(gridDim.x) * 2 * COUNT;
+      for (int w = threadIdx.x; w < words; w += blockDim.x) {
+        const int b = w / (2 * COUNT), j = w % (2 * COUNT);
+        const volatile unsigned long long* src = mailbox + b * (2 * kGpReduceValues) + j;
+        unsigned long long got = *src;
+        for (int spins = 0; static_cast<uint32_t>(got >> 32) != epoch && spins < kGpSpinLimit; spins++) got = *src;
+        if (static_cast<uint32_t>(got >> 32) != epoch) *abort_flag = 1;
+        reinterpret_cast<uint32_t*>(landed[b])[j] = static_cast<uint32_t>(got);
+      }
+      __syncthreads();
+      // (the next write into `landed` comes after the next reduction's first barrier, which
+      //  every thread reaches only after these reads)
+      if (*abort_flag) {
+        dead = true;
+        if (threadIdx.x == 0) {
+          p.status[0] = kGpFaultBarrierTimeout;
+          p.status[1] = static_cast<int32_t>(epoch);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < COUNT; i++) {
-        double total = __ldcg(mailbox + i);
-        for (unsigned b = 1; b < gridDim.x; b++) {
-          const double other = __ldcg(mailbox + b * 4 + i);
-          total = is_max[i] ? fmax(total, other) : total + other;
-        }
-        values[i] = total;
+        unsigned long long total = landed[0][i];
+        for (unsigned b = 1; b < gridDim.x; b++) total = combine(total, landed[b][i]);
+        bits[i] = total;
       }
     }
   }
-  __device__ double Sum(double v) {
-    double values[1] = {v};
-    const bool is_max[1] = {false};
-    All<1>(values, is_max);
-    return values[0];
+  template <int COUNT>
+  __device__ void MaxKeys(unsigned long long (&keys)[COUNT]) {
+    Exchange<COUNT, true>(keys);
   }
+  __device__ double Sum(double v) {
+    unsigned long long bits[1] = {static_cast<unsigned long long>(__double_as_longlong(v))};
+    Exchange<1, false>(bits);
+    return __longlong_as_double(static_cast<long long>(bits[0]));
+  }
+  // Every thread of the launch has got here.
+  __device__ void Barrier() { Sum(0.0); }
 };
 
-__global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const GpParams p) {
-  __shared__ double reduce_smem[32][4];
+// One element of P(t) = V diag(exp(lambda t)) V^-1 per lane, computed by a half-warp:
+// lane (i, j) = ((lane >> 2) & 3, lane & 3) of either half returns P_ij.  The four
+// exponentials are computed once per half-warp (lanes 0..3 of the half) and exchanged by
+// shuffles -- the fp64 exp is ~45 instructions and a whole CTA shares one SM's fp64 pipe,
+// so the interpreter never lets every thread evaluate it redundantly.  Same operation
+// order per element as TransitionMatrix.
+__device__ __forceinline__ double HalfWarpTransitionElement(const GpParams& p, double t) {
+  const int lane = threadIdx.x & 31;
+  const double mine = exp(t * p.eval[lane & 3]);
+  const int i = (lane >> 2) & 3, j = lane & 3, base = lane & 16;
+  double sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double d = __shfl_sync(0xffffffffu, mine, base + k);
+    sum += (p.evec[i * 4 + k] * d) * p.ivec[k * 4 + j];
+  }
+  return sum;
+}
+
+// Shared-memory plan of the interpreter (dynamic; what does not fit stays in global memory).
+struct GpSmemPlan {
+  int32_t program_words;  // the op program, staged once (0: read from global memory)
+  int32_t matrices;       // P(t_g) of every GPCSP + a copy of q: [gpcsp][16], [gpcsp]
+  int32_t counts;         // rescaling counts, one copy per warp: [warp][plv]
+  int32_t scratch;        // doubles of UpdateSBNProbabilities scratch
+  size_t bytes;
+};
+
+// SINGLE: every thread owns at most one site pattern (the launch has at least as many threads
+// as patterns) -- the pattern loops of the ops disappear.
+template <bool SINGLE>
+__global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const GpParams p, const GpSmemPlan plan) {
+  extern __shared__ __align__(16) unsigned char gp_smem[];
+  __shared__ unsigned long long reduce_smem[2][kGpMaxBlockThreads / 32][kGpReduceValues];
+  __shared__ unsigned long long landed_smem[kGpMaxGridBlocks][kGpReduceValues];
+  __shared__ int abort_flag;
+  __shared__ __align__(16) double warp_matrix_smem[kGpMaxBlockThreads / 32][16];
+  if (threadIdx.x == 0) abort_flag = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = (blockDim.x + 31) >> 5;
+  const int G = p.gpcsp_count;
+  // ---- carve-up: [matrices | q | scratch | counts | program]
+  double* const matrices_smem = reinterpret_cast<double*>(gp_smem);
+  double* const q_smem = matrices_smem + (plan.matrices ? static_cast<size_t>(G) * 16 : 0);
+  double* const scratch = q_smem + (plan.matrices ? G : 0);
+  int32_t* const counts_smem = reinterpret_cast<int32_t*>(scratch + plan.scratch);
+  int32_t* const program_smem = counts_smem + (plan.counts ? static_cast<size_t>(warps) * p.plv_count : 0);
+
   // The op program is a dependency chain: every op starts by reading its own words.  A
-  // program of up to kGpProgramSmemWords words (the DS1 DAG's sweeps are ~5.5 k) is staged
-  // in shared memory once, so that read is an LDS instead of a global round trip per op.
-  __shared__ int32_t program_smem[kGpProgramSmemWords];
+  // program that fits is staged in shared memory once, so that read is an LDS instead of
+  // a global round trip per op.
   const int32_t* program = p.program;
-  if (p.word_count <= kGpProgramSmemWords) {
+  if (plan.program_words > 0) {
     for (int64_t w = threadIdx.x; w < p.word_count; w += blockDim.x) program_smem[w] = p.program[w];
-    __syncthreads();
     program = program_smem;
   }
-  Reducer reduce{p, gridDim.x > 1, 0, reduce_smem};
+  // Transition matrices of all GPCSPs at their current branch lengths: computed once per
+  // launch by half-warps, kept current by OptimizeBranchLength.  (Every thread of the CTA
+  // evaluating V exp(Lambda t) V^-1 for itself cost ~290 fp64 instructions per op -- on
+  // ONE SM's fp64 pipe that was most of an op's 2 us.)
+  double* const matrices = plan.matrices ? matrices_smem : p.matrix_cache;
+  double* const q = plan.matrices ? q_smem : p.q;
+  for (int g0 = warp * 2; g0 < G; g0 += warps * 2) {
+    const int g = min(g0 + (lane >> 4), G - 1);  // (an odd tail: both halves compute the same matrix)
+    const double element = HalfWarpTransitionElement(p, p.branch_lengths[g]);
+    matrices[static_cast<size_t>(g) * 16 + (lane & 15)] = element;
+  }
+  if (plan.matrices)
+    for (int g = threadIdx.x; g < G; g += blockDim.x) q_smem[g] = p.q[g];
+  // Warps drift apart between reductions, so a shared copy of the rescaling
+  // counts could show a lagging warp a value from its future; every warp keeps
+  // (and redundantly updates) its own copy.  Branch lengths, matrices and q are only
+  // written right after a barrier of the same op, which orders them after every
+  // older read, and every warp writes the same bits.
+  int32_t* const counts =
+      plan.counts ? counts_smem + static_cast<size_t>(warp) * p.plv_count
+                  : p.counts + (static_cast<size_t>(blockIdx.x) * (kGpMaxBlockThreads / 32) + warp) * p.plv_count;
+  if (plan.counts)
+    for (int i = lane; i < p.plv_count; i += 32) counts[i] = p.counts[i];
+  // (the first copy in global memory is what the getters and the other kernels read)
+  const bool mirrors_counts = plan.counts && blockIdx.x == 0 && warp == 0;
+  auto set_count = [&](int index, int value) {
+    counts[index] = value;
+    if (mirrors_counts) p.counts[index] = value;
+  };
+  __syncthreads();
+
+  Reducer reduce{p, gridDim.x > 1, reduce_smem, landed_smem, &abort_flag};
   const int64_t P = p.pattern_count;
   const int64_t first = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  // Warps drift apart between reductions, so a shared copy of the rescaling
-  // counts could show a lagging warp a value from its future; every warp keeps
-  // (and redundantly updates) its own copy.  Branch lengths and q are only
-  // written right after a barrier of the same op, which orders them after every
-  // older read.
-  int32_t* counts = p.counts + (static_cast<size_t>(blockIdx.x) * (kGpMaxBlockThreads / 32) + (threadIdx.x >> 5)) *
-                                   p.plv_count;
+  // This thread's patterns: first, first + stride, ... (SINGLE: at most `first`).
+  const int64_t step = SINGLE ? P : stride;
   auto plv = [&](int index) -> double* { return p.plvs + static_cast<size_t>(index) * P * 4; };
   auto fault = [&](int code, int64_t pc) {
     if (first == 0) {
@@ -233,11 +386,35 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
       p.status[1] = static_cast<int32_t>(pc);
     }
   };
-  // sum_k w_k (log(rootward_k^T M leafward_k) + count_log) for OptimizeBranchLength
+  auto load_matrix = [&](int gpcsp, double (&m)[16]) {
+    const double2* src = reinterpret_cast<const double2*>(matrices + static_cast<size_t>(gpcsp) * 16);
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+      const double2 v = src[x];
+      m[2 * x] = v.x, m[2 * x + 1] = v.y;
+    }
+  };
+  // P(t) for every lane of the warp: one element per lane of a half-warp, exchanged through
+  // the warp's 16 doubles of shared memory.
+  auto warp_transition_matrix = [&](double t, double (&m)[16]) {
+    const double element = HalfWarpTransitionElement(p, t);
+    double* const mine = warp_matrix_smem[warp];
+    __syncwarp();  // (the previous evaluation's reads)
+    if (lane < 16) mine[lane] = element;
+    __syncwarp();
+    const double2* src = reinterpret_cast<const double2*>(mine);
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+      const double2 v = src[x];
+      m[2 * x] = v.x, m[2 * x + 1] = v.y;
+    }
+  };
+  // sum_k w_k (log(rootward_k^T P(t) leafward_k) + count_log): the general form of
+  // OptimizeBranchLength's objective (any number of patterns per thread).
   auto edge_log_likelihood = [&](const double* rootward, const double* leafward, double t,
                                  double count_log) -> double {
     double m[16];
-    TransitionMatrix(p, t, false, m);
+    warp_transition_matrix(t, m);
     double local = 0.0;
     for (int64_t k = first; k < P; k += stride) {
       double r[4], l[4];
@@ -249,121 +426,251 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
   };
 
   int64_t pc = 0;
-  while (pc < p.word_count) {
-    const int opcode = program[pc];
+  while (pc < p.word_count && !reduce.dead) {
+    // Word 0 of a record: opcode | batch << 8.  A batch is a run of `batch` records of the
+    // same kind that the host found mutually independent (CompileProgram below): their
+    // loads are issued together, and their reductions travel in one exchange.
+    const int word0 = program[pc];
+    const int opcode = word0 & 0xff;
+    const int batch = max(word0 >> 8, 1);
     switch (opcode) {
       case SBNB_GP_ZERO_PLV: {  // gp_engine.cpp:48-51
-        const int dest = program[pc + 1];
         const double zero[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int64_t k = first; k < P; k += stride) StoreState(plv(dest), k, zero);
-        counts[dest] = 0;
-        pc += 2;
+        for (int u = 0; u < batch; u++) {
+          const int dest = program[pc + 2 * u + 1];
+          for (int64_t k = first; k < P; k += step) StoreState(plv(dest), k, zero);
+          set_count(dest, 0);
+        }
+        pc += 2 * batch;
         break;
       }
       case SBNB_GP_SET_TO_STATIONARY: {  // gp_engine.cpp:53-62
-        const int dest = program[pc + 1], root = program[pc + 2];
-        const double prior = p.q[root];
-        const double x[4] = {prior * p.freqs[0], prior * p.freqs[1], prior * p.freqs[2], prior * p.freqs[3]};
-        for (int64_t k = first; k < P; k += stride) StoreState(plv(dest), k, x);
-        counts[dest] = 0;
-        pc += 3;
+        for (int u = 0; u < batch; u++) {
+          const int dest = program[pc + 3 * u + 1], root = program[pc + 3 * u + 2];
+          const double prior = q[root];
+          const double x[4] = {prior * p.freqs[0], prior * p.freqs[1], prior * p.freqs[2], prior * p.freqs[3]};
+          for (int64_t k = first; k < P; k += step) StoreState(plv(dest), k, x);
+          set_count(dest, 0);
+        }
+        pc += 3 * batch;
         break;
       }
       case SBNB_GP_INCREMENT_WITH_EVOLVED: {  // gp_engine.cpp:64-82
-        const int dest = program[pc + 1], gpcsp = program[pc + 2], src = program[pc + 3];
-        const int difference = counts[src] - counts[dest];
-        if (difference < 0) {
-          fault(kGpFaultDestRescaling, pc);
+        double* dest_plv[kGpBatch];
+        const double* src_plv[kGpBatch];
+        int gpcsp[kGpBatch];
+        double factor[kGpBatch];
+        int faulty = -1;  // (no return inside the unrolled loops: they must stay unrolled for the arrays to be registers)
+#pragma unroll
+        for (int u = 0; u < kGpBatch; u++) {
+          if (u < batch) {
+            const int dest = program[pc + 4 * u + 1], src = program[pc + 4 * u + 3];
+            gpcsp[u] = program[pc + 4 * u + 2];
+            dest_plv[u] = plv(dest);
+            src_plv[u] = plv(src);
+            const int difference = counts[src] - counts[dest];
+            if (difference < 0 && faulty < 0) faulty = u;
+            factor[u] = q[gpcsp[u]];
+            if (difference > 0) factor[u] *= pow(p.threshold, static_cast<double>(difference));
+          }
+        }
+        if (faulty >= 0) {
+          fault(kGpFaultDestRescaling, pc + 4 * faulty);
           return;
         }
-        const double factor =
-            (difference == 0 ? 1.0 : pow(p.threshold, static_cast<double>(difference))) * p.q[gpcsp];
-        double m[16];
-        TransitionMatrix(p, p.branch_lengths[gpcsp], false, m);
-        for (int64_t k = first; k < P; k += stride) {
-          double s[4], d[4];
-          LoadState(plv(src), k, s);
-          LoadState(plv(dest), k, d);
+        for (int64_t k = first; k < P; k += step) {
+          double s[kGpBatch][4], d[kGpBatch][4];
 #pragma unroll
-          for (int i = 0; i < 4; i++)
-            d[i] += factor * fma(m[i * 4 + 3], s[3], fma(m[i * 4 + 2], s[2], fma(m[i * 4 + 1], s[1], m[i * 4] * s[0])));
-          StoreState(plv(dest), k, d);
+          for (int u = 0; u < kGpBatch; u++) {
+            if (u < batch) {
+              LoadState(src_plv[u], k, s[u]);
+              LoadState(dest_plv[u], k, d[u]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kGpBatch; u++) {
+            if (u < batch) {
+              double m[16];
+              load_matrix(gpcsp[u], m);
+#pragma unroll
+              for (int i = 0; i < 4; i++)
+                d[u][i] += factor[u] * fma(m[i * 4 + 3], s[u][3],
+                                           fma(m[i * 4 + 2], s[u][2], fma(m[i * 4 + 1], s[u][1], m[i * 4] * s[u][0])));
+              StoreState(dest_plv[u], k, d[u]);
+              // (keeps the next op's matrix loads from being hoisted above this point: four
+              //  matrices live at once cost 128 registers and spill)
+              asm volatile("" ::: "memory");
+            }
+          }
         }
-        pc += 4;
+        pc += 4 * batch;
         break;
       }
       case SBNB_GP_MULTIPLY: {  // gp_engine.cpp:111-117 + RescalePLVIfNeeded 298-320
-        const int dest = program[pc + 1], src1 = program[pc + 2], src2 = program[pc + 3];
-        int count = counts[src1] + counts[src2];
-        double values[3] = {0.0, 0.0, 0.0};  // max entry, max of -entry, non-finite flag
-        for (int64_t k = first; k < P; k += stride) {
-          double a[4], b[4], d[4];
-          LoadState(plv(src1), k, a);
-          LoadState(plv(src2), k, b);
+        double* dest_plv[kGpBatch];
+        const double *a_plv[kGpBatch], *b_plv[kGpBatch];
+        // per op, as sortable keys: the largest entry, and (complemented) the smallest
+        unsigned long long keys[2 * kGpBatch];
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            d[i] = a[i] * b[i];
-            values[0] = fmax(values[0], d[i]);
-            values[1] = fmax(values[1], -d[i]);
-            if (!isfinite(d[i])) values[2] = 1.0;
+        for (int u = 0; u < kGpBatch; u++) {
+          keys[2 * u] = keys[2 * u + 1] = 0;
+          if (u < batch) {
+            dest_plv[u] = plv(program[pc + 4 * u + 1]);
+            a_plv[u] = plv(program[pc + 4 * u + 2]);
+            b_plv[u] = plv(program[pc + 4 * u + 3]);
           }
-          StoreState(plv(dest), k, d);
         }
-        const bool is_max[3] = {true, true, true};
-        reduce.All<3>(values, is_max);
-        if (values[2] != 0.0) {
-          fault(kGpFaultNotFinite, pc);
-          return;
-        }
-        if (values[1] > 0.0) {
-          fault(kGpFaultNegative, pc);
-          return;
-        }
-        double max_entry = values[0];
-        if (max_entry != 0.0) {
-          int rescaling = 0;
-          while (max_entry < p.threshold) {
-            max_entry /= p.threshold;
-            rescaling++;
-          }
-          if (rescaling > 0) {
-            const double divisor = pow(p.threshold, static_cast<double>(rescaling));
-            for (int64_t k = first; k < P; k += stride) {
-              double d[4];
-              LoadState(plv(dest), k, d);
+        for (int64_t k = first; k < P; k += step) {
+          double a[kGpBatch][4], b[kGpBatch][4];
 #pragma unroll
-              for (int i = 0; i < 4; i++) d[i] /= divisor;
-              StoreState(plv(dest), k, d);
+          for (int u = 0; u < kGpBatch; u++) {
+            if (u < batch) {
+              LoadState(a_plv[u], k, a[u]);
+              LoadState(b_plv[u], k, b[u]);
             }
-            count += rescaling;
+          }
+#pragma unroll
+          for (int u = 0; u < kGpBatch; u++) {
+            if (u < batch) {
+              double d[4];
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                d[i] = a[u][i] * b[u][i];
+                const unsigned long long key = SortableKey(d[i]);
+                keys[2 * u] = key > keys[2 * u] ? key : keys[2 * u];
+                keys[2 * u + 1] = ~key > keys[2 * u + 1] ? ~key : keys[2 * u + 1];
+              }
+              StoreState(dest_plv[u], k, d);
+            }
           }
         }
-        counts[dest] = count;
-        pc += 4;
+        if (batch == 1) {
+          unsigned long long pair[2] = {keys[0], keys[1]};
+          reduce.MaxKeys<2>(pair);
+          keys[0] = pair[0], keys[1] = pair[1];
+        } else {
+          reduce.MaxKeys<2 * kGpBatch>(keys);
+        }
+        int faulty = -1, fault_code = kGpOk;
+#pragma unroll
+        for (int u = 0; u < kGpBatch; u++) {
+          if (u < batch && faulty < 0) {
+            // (keys of +inf and NaN sit above every finite value; a thread without a pattern left 0)
+            if (keys[2 * u] >= SortableKey(INFINITY)) {
+              faulty = u, fault_code = kGpFaultNotFinite;
+            } else if (keys[2 * u + 1] != 0 && ~keys[2 * u + 1] < SortableKey(-0.0)) {
+              faulty = u;
+              fault_code = ~keys[2 * u + 1] <= SortableKey(-INFINITY) ? kGpFaultNotFinite : kGpFaultNegative;
+            }
+          }
+        }
+        if (faulty >= 0) {
+          fault(fault_code, pc + 4 * faulty);
+          return;
+        }
+#pragma unroll
+        for (int u = 0; u < kGpBatch; u++) {
+          if (u < batch) {
+            const int dest = program[pc + 4 * u + 1], src1 = program[pc + 4 * u + 2], src2 = program[pc + 4 * u + 3];
+            int count = counts[src1] + counts[src2];
+            double max_entry = keys[2 * u] == 0 ? 0.0 : FromSortableKey(keys[2 * u]);
+            if (max_entry != 0.0 && max_entry < p.threshold) {
+              int rescaling = 0;
+              while (max_entry < p.threshold) {
+                max_entry /= p.threshold;
+                rescaling++;
+              }
+              const double divisor = pow(p.threshold, static_cast<double>(rescaling));
+              for (int64_t k = first; k < P; k += step) {
+                double d[4];
+                LoadState(dest_plv[u], k, d);
+#pragma unroll
+                for (int i = 0; i < 4; i++) d[i] /= divisor;
+                StoreState(dest_plv[u], k, d);
+              }
+              count += rescaling;
+            }
+            set_count(dest, count);
+          }
+        }
+        pc += 4 * batch;
         break;
       }
       case SBNB_GP_LIKELIHOOD: {  // gp_engine.cpp:119-123, gp_engine.hpp:198-206
-        const int dest = program[pc + 1], child = program[pc + 2], parent = program[pc + 3];
-        double m[16];
-        TransitionMatrix(p, p.branch_lengths[dest], false, m);
-        const double count_log = static_cast<double>(counts[parent]) * p.log_threshold +
-                                 static_cast<double>(counts[child]) * p.log_threshold;
-        double* row = p.log_likelihoods + static_cast<size_t>(dest) * P;
-        for (int64_t k = first; k < P; k += stride) {
-          double a[4], b[4];
-          LoadState(plv(parent), k, a);
-          LoadState(plv(child), k, b);
-          row[k] = log(Bilinear(a, m, b)) + count_log;
+        const double *parent_plv[kGpBatch], *child_plv[kGpBatch];
+        double* row[kGpBatch];
+        int dest[kGpBatch];
+        double count_log[kGpBatch];
+#pragma unroll
+        for (int u = 0; u < kGpBatch; u++) {
+          if (u < batch) {
+            dest[u] = program[pc + 4 * u + 1];
+            const int child = program[pc + 4 * u + 2], parent = program[pc + 4 * u + 3];
+            parent_plv[u] = plv(parent);
+            child_plv[u] = plv(child);
+            row[u] = p.log_likelihoods + static_cast<size_t>(dest[u]) * P;
+            count_log[u] = static_cast<double>(counts[parent]) * p.log_threshold +
+                           static_cast<double>(counts[child]) * p.log_threshold;
+          }
         }
-        pc += 4;
+        for (int64_t k = first; k < P; k += step) {
+          double a[kGpBatch][4], b[kGpBatch][4];
+#pragma unroll
+          for (int u = 0; u < kGpBatch; u++) {
+            if (u < batch) {
+              LoadState(parent_plv[u], k, a[u]);
+              LoadState(child_plv[u], k, b[u]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kGpBatch; u++) {
+            if (u < batch) {
+              double m[16];
+              load_matrix(dest[u], m);
+              row[u][k] = log(Bilinear(a[u], m, b[u])) + count_log[u];
+              asm volatile("" ::: "memory");
+            }
+          }
+        }
+        pc += 4 * batch;
         break;
       }
       case SBNB_GP_OPTIMIZE_BRANCH_LENGTH: {  // gp_engine.cpp:326-345, optimization.hpp:10-115
         const int leafward = program[pc + 1], rootward = program[pc + 2], gpcsp = program[pc + 3];
         const double count_log = static_cast<double>(counts[rootward]) * p.log_threshold +
                                  static_cast<double>(counts[leafward]) * p.log_threshold;
+        // The thread's own patterns stay in registers for the whole search when there are at
+        // most kOwn of them (the matrix form r^T P(t) l of the reference, gp_engine.cpp:244-266:
+        // evaluated in the eigenbasis instead -- 4 fma per pattern -- the objective differs in
+        // its last bits, and on the DS1 DAG that was enough to send one of Brent's searches
+        // down another path: a 7e-5 relative change in the sum of the branch lengths after six
+        // sweeps; measured, and dropped for 12 % of the sweep's time).
+        constexpr int kOwn = SINGLE ? 1 : 2;
+        const bool own_cover = P <= kOwn * stride;
+        double r[kOwn][4], l[kOwn][4], weight[kOwn];
+        if (own_cover) {
+#pragma unroll
+          for (int s = 0; s < kOwn; s++) {
+            const int64_t k = first + s * stride;
+            weight[s] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) r[s][i] = l[s][i] = 1.0;  // (no pattern: log of a positive number x weight 0)
+            if (k < P) {
+              LoadState(plv(rootward), k, r[s]);
+              LoadState(plv(leafward), k, l[s]);
+              weight[s] = p.weights[k];
+            }
+          }
+        }
         auto f = [&](double log_branch_length) -> double {
-          return -edge_log_likelihood(plv(rootward), plv(leafward), exp(log_branch_length), count_log);
+          const double t = exp(log_branch_length);
+          if (!own_cover) return -edge_log_likelihood(plv(rootward), plv(leafward), t, count_log);
+          double m[16];
+          warp_transition_matrix(t, m);
+          double local = 0.0;
+#pragma unroll
+          for (int s = 0; s < kOwn; s++) local = fma(weight[s], log(Bilinear(r[s], m, l[s])) + count_log, local);
+          return -reduce.Sum(local);
         };
         const double current_log_branch_length = log(p.branch_lengths[gpcsp]);
         const double current_value = f(current_log_branch_length);
@@ -434,51 +741,60 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
           }
         } while (--count);
         // "Numerical optimization sometimes yields new nllk > current nllk."
-        p.branch_lengths[gpcsp] = (fx > current_value) ? exp(current_log_branch_length) : exp(x);
+        // (every warp has passed the last evaluation's barrier: nobody still reads the old values)
+        const double new_length = (fx > current_value) ? exp(current_log_branch_length) : exp(x);
+        p.branch_lengths[gpcsp] = new_length;
+        {
+          const double element = HalfWarpTransitionElement(p, new_length);
+          if (lane < 16) matrices[static_cast<size_t>(gpcsp) * 16 + lane] = element;
+          __syncwarp();
+        }
         pc += 4;
         break;
       }
       case SBNB_GP_UPDATE_SBN_PROBABILITIES: {  // gp_engine.cpp:136-153
         const int start = program[pc + 1], stop = program[pc + 2];
         const int length = stop - start;
+        auto set_q = [&](int g, double value) {
+          q[g] = value;
+          if (plan.matrices) p.q[g] = value;  // (the copy the getters read)
+        };
         if (length == 1) {
-          __syncthreads();  // lagging warps may still be reading q in an older op
-          if (gridDim.x > 1) cg::this_grid().sync();
-          p.q[start] = 1.0;
+          reduce.Barrier();  // lagging warps may still be reading q in an older op
+          set_q(start, 1.0);
         } else if (length > 1) {
+          // (a lagging warp may still be reading the scratch values of an older op)
+          __syncthreads();
           bool use_hybrid = true;
           for (int g = start; g < stop; g++) use_hybrid = use_hybrid && (p.hybrid[g] > -INFINITY);
-          // log of the unnormalised posterior per GPCSP, folded with LogAdd in index order
+          // weighted sum of a GPCSP's per-pattern log likelihoods
+          auto row_sum = [&](int g) -> double {
+            const double* row = p.log_likelihoods + static_cast<size_t>(g) * P;
+            double local = 0.0;
+            for (int64_t k = first; k < P; k += stride) local = fma(row[k], p.weights[k], local);
+            return reduce.Sum(local);
+          };
+          // log of the unnormalised posterior per GPCSP, folded with LogAdd in index order;
+          // kept for the second pass when the scratch holds the range (every thread writes
+          // the same bits)
+          const bool keep = length <= plan.scratch;
           double log_norm = 0.0;
           for (int g = start; g < stop; g++) {
-            double log_likelihood;
-            if (use_hybrid) {
-              log_likelihood = p.hybrid[g];
-            } else {
-              const double* row = p.log_likelihoods + static_cast<size_t>(g) * P;
-              double local = 0.0;
-              for (int64_t k = first; k < P; k += stride) local = fma(row[k], p.weights[k], local);
-              log_likelihood = reduce.Sum(local);
-            }
-            const double value = log_likelihood + log(p.q[g]);
+            const double value = (use_hybrid ? p.hybrid[g] : row_sum(g)) + log(q[g]);
+            if (keep) scratch[g - start] = value;
             log_norm = (g == start) ? value : LogAdd(log_norm, value);
           }
-          // second pass recomputes the same values (identical bits) and normalises
-          for (int g = start; g < stop; g++) {
-            double log_likelihood;
-            if (use_hybrid) {
-              log_likelihood = p.hybrid[g];
-            } else {
-              const double* row = p.log_likelihoods + static_cast<size_t>(g) * P;
-              double local = 0.0;
-              for (int64_t k = first; k < P; k += stride) local = fma(row[k], p.weights[k], local);
-              log_likelihood = reduce.Sum(local);
+          if (keep) {
+            // every thread must have read q[start..stop) before anyone overwrites it
+            reduce.Barrier();
+            for (int g = start; g < stop; g++) set_q(g, exp(scratch[g - start] - log_norm));
+          } else {
+            // too long for the scratch: the second pass recomputes the same values (identical bits)
+            for (int g = start; g < stop; g++) {
+              const double updated = exp((use_hybrid ? p.hybrid[g] : row_sum(g)) + log(q[g]) - log_norm);
+              reduce.Barrier();
+              set_q(g, updated);
             }
-            const double updated = exp(log_likelihood + log(p.q[g]) - log_norm);
-            // every thread must have read q[g] before anyone overwrites it
-            __syncthreads();
-            if (gridDim.x > 1) cg::this_grid().sync();
-            p.q[g] = updated;
           }
         }
         pc += 3;
@@ -496,7 +812,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
           return;
         }
         const double count_log = static_cast<double>(counts[leafward]) * p.log_threshold;
-        const double log_prior = log(p.q[rootsplit]);
+        const double log_prior = log(q[rootsplit]);
         double* row = p.log_likelihoods + static_cast<size_t>(rootsplit) * P;
         for (int64_t k = first; k < P; k += stride) {
           double a[4], b[4];
@@ -513,7 +829,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         const int dest = program[pc + 1], src_count = program[pc + 2];
         int minimum = counts[program[pc + 3]];
         for (int i = 1; i < src_count; i++) minimum = min(minimum, counts[program[pc + 3 + i]]);
-        counts[dest] = minimum;
+        set_count(dest, minimum);
         pc += 3 + src_count;
         break;
       }
@@ -523,6 +839,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
     }
   }
 }
+
 
 // GetLogMarginalLikelihood, GetPerGPCSPLogLikelihoods: rows[r] . weights, one block per row.
 __global__ void GpWeightedRowSumsKernel(const double* rows, const double* weights, int64_t P, double* out) {
@@ -665,6 +982,8 @@ const char* FaultMessage(int code) {
       return "Multiply dest_ is not finite";
     case kGpFaultNegative:
       return "PLV with negative entry passed to RescalePLVIfNeeded";
+    case kGpFaultBarrierTimeout:
+      return "libsbn_b200: a thread block of the GP interpreter never reached a reduction (device barrier timed out)";
     default:
       return "Malformed GP operation program";
   }
@@ -675,6 +994,28 @@ const char* FaultMessage(int code) {
 }  // namespace sbnb
 
 using namespace sbnb;
+
+namespace {
+
+// The op program as the interpreter runs it.  The reference's schedules are long
+// sequences in which most neighbours do not depend on each other (DS1 DAG: the 1410 ops that
+// populate the PLVs form 66 dependency levels), and on the device an op is a chain of
+// latencies, not of arithmetic.  So the program is re-ordered by dependency level -- an op's
+// level is one more than the highest level among the ops it must follow (read after write,
+// write after write, write after read, over PLVs, rescaling counts, q, branch lengths,
+// log-likelihood rows and the log-marginal vector) -- and, inside a level, by kind; runs of
+// one kind become batches whose loads the interpreter issues together and whose reductions
+// share one exchange.  Ops of one level are independent, so every value is computed by the
+// same arithmetic in the same order as in the reference's sequence: bit-identical results.
+struct CompiledProgram {
+  std::vector<int32_t> source;  // the caller's words (cache key)
+  std::vector<int32_t> words;   // what the device runs
+  std::vector<std::pair<int32_t, int32_t>> origin;  // (word offset in `words`, word offset in `source`) per op
+  DeviceArray<int32_t> device;
+  uint64_t last_used = 0;
+};
+
+}  // namespace
 
 struct sbnb_gp_engine {
   int device = 0;
@@ -687,7 +1028,12 @@ struct sbnb_gp_engine {
   GpParams params{};
   DeviceArray<double> plvs, branch_lengths, q, hybrid, log_likelihoods, log_marginal, weights, exchange, scalars,
       node_probabilities, inverted_prior;
+  DeviceArray<double> matrix_cache;
   DeviceArray<int32_t> counts, program, status, tips;
+  // programs seen before (the reference regenerates the same few schedules call after call)
+  std::vector<std::unique_ptr<CompiledProgram>> compiled;
+  uint64_t program_clock = 0;
+  GpSmemPlan plan{};  // the per-engine part (matrices, counts, scratch); the program is fitted per launch
   bool has_node_probabilities = false;
   int64_t launch_count = 0;
   double last_kernel_ms = 0.0;
@@ -701,6 +1047,9 @@ struct sbnb_gp_engine {
 
 namespace {
 
+void CompileProgram(int32_t plv_count, int32_t gpcsp_count, const int32_t* program, int64_t word_count,
+                    CompiledProgram* out);
+
 void Bind(sbnb_gp_engine* e) { SBNB_CUDA(cudaSetDevice(e->device)); }
 
 void CopyOut(sbnb_gp_engine* e, double* host, const double* device, size_t count) {
@@ -708,15 +1057,18 @@ void CopyOut(sbnb_gp_engine* e, double* host, const double* device, size_t count
   SBNB_CUDA(cudaStreamSynchronize(e->stream));
 }
 
-void CheckPlv(const sbnb_gp_engine* e, int index) {
-  Require(index >= 0 && index < e->plv_count, "PLV index out of range.");
+struct GpShape {
+  int32_t plv_count, gpcsp_count;
+};
+void CheckPlv(const GpShape& e, int index) { Require(index >= 0 && index < e.plv_count, "PLV index out of range."); }
+void CheckGpcsp(const GpShape& e, int index) {
+  Require(index >= 0 && index < e.gpcsp_count, "GPCSP index out of range.");
 }
-void CheckGpcsp(const sbnb_gp_engine* e, int index) {
-  Require(index >= 0 && index < e->gpcsp_count, "GPCSP index out of range.");
-}
+void CheckPlv(const sbnb_gp_engine* e, int index) { CheckPlv(GpShape{e->plv_count, e->gpcsp_count}, index); }
+void CheckGpcsp(const sbnb_gp_engine* e, int index) { CheckGpcsp(GpShape{e->plv_count, e->gpcsp_count}, index); }
 
 // Host-side validation of a program: every index in range, records complete.
-void ValidateProgram(const sbnb_gp_engine* e, const int32_t* program, int64_t words) {
+void ValidateProgram(const GpShape& e, const int32_t* program, int64_t words) {
   int64_t pc = 0;
   while (pc < words) {
     const int opcode = program[pc];
@@ -761,7 +1113,7 @@ void ValidateProgram(const sbnb_gp_engine* e, const int32_t* program, int64_t wo
         break;
       case SBNB_GP_UPDATE_SBN_PROBABILITIES:
         need(3);
-        Require(program[pc + 1] >= 0 && program[pc + 1] <= program[pc + 2] && program[pc + 2] <= e->gpcsp_count,
+        Require(program[pc + 1] >= 0 && program[pc + 1] <= program[pc + 2] && program[pc + 2] <= e.gpcsp_count,
                 "UpdateSBNProbabilities range out of bounds.");
         pc += 3;
         break;
@@ -789,6 +1141,13 @@ void ValidateProgram(const sbnb_gp_engine* e, const int32_t* program, int64_t wo
         Fail(SBNB_ERR_INVALID_ARGUMENT, "Unknown GP opcode " + std::to_string(opcode) + ".");
     }
   }
+}
+
+// Where in the caller's program the op at `offset` of the compiled program came from.
+int32_t OriginalOffset(const CompiledProgram& compiled, int32_t offset) {
+  for (const auto& entry : compiled.origin)
+    if (entry.first == offset) return entry.second;
+  return offset;
 }
 
 void WeightedRowSums(sbnb_gp_engine* e, const double* rows, int row_count, double* host_out) {
@@ -845,6 +1204,132 @@ void QuartetLikelihoods(sbnb_gp_engine* e, int32_t central, const int32_t* rootw
     Fail(SBNB_ERR_GP_ASSERT, "Rescaling not implemented in CalculateQuartetHybridLikelihoods.");
 }
 
+void CompileProgram(int32_t plv_count, int32_t gpcsp_count, const int32_t* program, int64_t word_count,
+                    CompiledProgram* out) {
+  struct Op {
+    int32_t at, words, opcode, level;
+  };
+  // last writer's level, and the highest level among the readers since, per resource
+  struct Track {
+    int32_t written = -1, read = -1;
+  };
+  const size_t gpcsps = std::max(gpcsp_count, 1);
+  std::vector<Track> plv(plv_count), count(plv_count), prior(gpcsps), length(gpcsps), row(gpcsps);
+  Track marginal;
+  std::vector<Op> ops;
+  int32_t level = 0;
+  auto reads = [&](Track& t) { level = std::max(level, t.written + 1); };
+  auto writes = [&](Track& t) { level = std::max(level, std::max(t.written, t.read) + 1); };
+  auto did_read = [&](Track& t) { t.read = std::max(t.read, level); };
+  auto did_write = [&](Track& t) {
+    t.written = level;
+    t.read = -1;
+  };
+  int64_t pc = 0;
+  while (pc < word_count) {
+    const int32_t* w = program + pc;
+    const int opcode = w[0];
+    int32_t size = 0;
+    level = 0;
+    // two passes over the op's resources: find its level, then record it
+    for (int pass = 0; pass < 2; pass++) {
+      auto R = [&](Track& t) { pass == 0 ? reads(t) : did_read(t); };
+      auto W = [&](Track& t) { pass == 0 ? writes(t) : did_write(t); };
+      switch (opcode) {
+        case SBNB_GP_ZERO_PLV:
+          size = 2;
+          W(plv[w[1]]), W(count[w[1]]);
+          break;
+        case SBNB_GP_SET_TO_STATIONARY:
+          size = 3;
+          R(prior[w[2]]), W(plv[w[1]]), W(count[w[1]]);
+          break;
+        case SBNB_GP_INCREMENT_WITH_EVOLVED:
+          size = 4;
+          R(plv[w[3]]), R(count[w[3]]), R(count[w[1]]), R(prior[w[2]]), R(length[w[2]]), R(plv[w[1]]), W(plv[w[1]]);
+          break;
+        case SBNB_GP_MULTIPLY:
+          size = 4;
+          R(plv[w[2]]), R(plv[w[3]]), R(count[w[2]]), R(count[w[3]]), W(plv[w[1]]), W(count[w[1]]);
+          break;
+        case SBNB_GP_LIKELIHOOD:
+          size = 4;
+          R(plv[w[2]]), R(plv[w[3]]), R(count[w[2]]), R(count[w[3]]), R(length[w[1]]), W(row[w[1]]);
+          break;
+        case SBNB_GP_OPTIMIZE_BRANCH_LENGTH:
+          size = 4;
+          R(plv[w[1]]), R(plv[w[2]]), R(count[w[1]]), R(count[w[2]]), R(length[w[3]]), W(length[w[3]]);
+          break;
+        case SBNB_GP_UPDATE_SBN_PROBABILITIES:
+          size = 3;
+          for (int g = w[1]; g < w[2]; g++) R(row[g]), R(prior[g]);
+          for (int g = w[1]; g < w[2]; g++) W(prior[g]);
+          break;
+        case SBNB_GP_RESET_MARGINAL_LIKELIHOOD:
+          size = 1;
+          W(marginal);
+          break;
+        case SBNB_GP_INCREMENT_MARGINAL:
+          size = 4;
+          R(plv[w[1]]), R(plv[w[3]]), R(count[w[1]]), R(count[w[3]]), R(prior[w[2]]), R(marginal), W(marginal),
+              W(row[w[2]]);
+          break;
+        case SBNB_GP_PREP_FOR_MARGINALIZATION:
+          size = 3 + w[2];
+          for (int i = 0; i < w[2]; i++) R(count[w[3 + i]]);
+          W(count[w[1]]);
+          break;
+        default:
+          Fail(SBNB_ERR_INVALID_ARGUMENT, "Unknown GP opcode " + std::to_string(opcode) + ".");
+      }
+    }
+    ops.push_back({static_cast<int32_t>(pc), size, opcode, level});
+    pc += size;
+  }
+  // by level, then kind (the scalar-only PrepForMarginalization first), then the reference's order
+  static const bool reorder = EnvInt("SBNB_GP_LEVELS", 1) != 0;
+  if (reorder)
+  std::stable_sort(ops.begin(), ops.end(), [](const Op& a, const Op& b) {
+    if (a.level != b.level) return a.level < b.level;
+    const int ka = a.opcode == SBNB_GP_PREP_FOR_MARGINALIZATION ? -1 : a.opcode;
+    const int kb = b.opcode == SBNB_GP_PREP_FOR_MARGINALIZATION ? -1 : b.opcode;
+    return ka < kb;
+  });
+  auto batch_limit = [](int opcode) {
+    switch (opcode) {
+      case SBNB_GP_ZERO_PLV:
+      case SBNB_GP_SET_TO_STATIONARY:
+        return 255;
+      case SBNB_GP_INCREMENT_WITH_EVOLVED:
+      case SBNB_GP_MULTIPLY:
+      case SBNB_GP_LIKELIHOOD:
+        return kGpBatch;
+      default:
+        return 1;
+    }
+  };
+  static const bool batching = EnvInt("SBNB_GP_BATCH", 1) != 0;
+  out->source.assign(program, program + word_count);
+  out->words.clear();
+  out->words.reserve(word_count);
+  out->origin.clear();
+  out->origin.reserve(ops.size());
+  for (size_t i = 0; i < ops.size();) {
+    size_t run = 1;
+    const int limit = batching ? batch_limit(ops[i].opcode) : 1;
+    while (reorder && i + run < ops.size() && static_cast<int>(run) < limit && ops[i + run].opcode == ops[i].opcode &&
+           ops[i + run].level == ops[i].level)
+      run++;
+    for (size_t r = 0; r < run; r++) {
+      const Op& op = ops[i + r];
+      out->origin.emplace_back(static_cast<int32_t>(out->words.size()), op.at);
+      out->words.insert(out->words.end(), program + op.at, program + op.at + op.words);
+      if (r == 0) out->words[out->words.size() - op.words] |= static_cast<int32_t>(run) << 8;
+    }
+    i += run;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -884,17 +1369,43 @@ int sbnb_gp_create(int32_t taxon_count, int64_t pattern_count, const uint8_t* ti
     SBNB_CUDA(cudaEventCreate(&e->begin));
     SBNB_CUDA(cudaEventCreate(&e->end));
     const int64_t P = pattern_count;
-    if (P <= kGpSingleBlockPatterns) {
-      e->blocks = 1;
-      e->threads = static_cast<int>(std::min<int64_t>((P + 31) / 32 * 32, kGpMaxBlockThreads));
-    } else {
-      e->threads = kGpGridBlockThreads;
-      int per_sm = 0;
-      SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, GpInterpretKernel, e->threads, 0));
-      const int64_t resident = static_cast<int64_t>(std::max(per_sm, 1)) * e->sm_count;
-      e->blocks = static_cast<int>(std::min<int64_t>((P + e->threads - 1) / e->threads, resident));
-    }
     const size_t gpcsps = std::max(gpcsp_count, 1);
+    // One site pattern per thread while the resident CTAs can hold them (an op is then a
+    // short dependency chain per thread, and the CTAs share the fp64 work of the SMs they
+    // sit on); strided patterns beyond that.
+    static const int forced_threads = EnvInt("SBNB_GP_THREADS", 0), forced_blocks = EnvInt("SBNB_GP_BLOCKS", 0);
+    const int max_blocks = std::min(kGpMaxGridBlocks, e->sm_count);
+    e->threads = P <= static_cast<int64_t>(kGpBlockThreads) * max_blocks
+                     ? static_cast<int>(std::min<int64_t>((P + 31) / 32 * 32, kGpBlockThreads))
+                     : kGpGridBlockThreads;
+    if (forced_threads > 0) e->threads = std::min(std::max(forced_threads / 32 * 32, 32), kGpMaxBlockThreads);
+    // Shared-memory plan, in the order of what an op touches most: the transition matrices
+    // (+ q), the per-warp rescaling counts, a scratch for UpdateSBNProbabilities; the op
+    // program takes what is left, launch by launch.
+    SBNB_CUDA(cudaFuncSetAttribute(GpInterpretKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(kGpSmemBudget)));
+    SBNB_CUDA(cudaFuncSetAttribute(GpInterpretKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(kGpSmemBudget)));
+    {
+      GpSmemPlan& plan = e->plan;
+      size_t used = 0;
+      const size_t matrix_bytes = gpcsps * 17 * sizeof(double);
+      plan.matrices = used + matrix_bytes <= kGpSmemBudget / 2;
+      if (plan.matrices) used += matrix_bytes;
+      plan.scratch = kGpScratchDoubles;
+      used += plan.scratch * sizeof(double);
+      const size_t count_bytes = static_cast<size_t>(e->threads / 32) * plv_count * sizeof(int32_t);
+      plan.counts = used + count_bytes <= kGpSmemBudget * 3 / 4;
+      if (plan.counts) used += count_bytes;
+      plan.bytes = used;
+    }
+    {
+      int per_sm = 0;
+      SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, GpInterpretKernel<false>, e->threads, kGpSmemBudget));
+      const int64_t resident = std::min<int64_t>(static_cast<int64_t>(std::max(per_sm, 1)) * e->sm_count, max_blocks);
+      e->blocks = static_cast<int>(std::min<int64_t>((P + e->threads - 1) / e->threads, resident));
+      if (forced_blocks > 0) e->blocks = std::min(e->blocks, forced_blocks);
+    }
     // PLVs: zero, then one-hot tips / all-ones gaps (gp_engine.cpp:268-286).
     {
       const size_t plv_doubles = static_cast<size_t>(plv_count) * P * 4;
@@ -929,7 +1440,8 @@ int sbnb_gp_create(int32_t taxon_count, int64_t pattern_count, const uint8_t* ti
     const size_t count_copies = static_cast<size_t>(e->blocks) * (kGpMaxBlockThreads / 32);
     e->counts.Reserve(count_copies * plv_count);
     SBNB_CUDA(cudaMemsetAsync(e->counts.get(), 0, count_copies * plv_count * sizeof(int32_t), e->stream));
-    e->exchange.Reserve(static_cast<size_t>(2) * e->blocks * 4);
+    e->exchange.Reserve(static_cast<size_t>(2) * e->blocks * 2 * kGpReduceValues);  // 8-byte words
+    e->matrix_cache.Reserve(gpcsps * 16);
     e->status.Reserve(2);
     if (unconditional_node_probabilities && inverted_sbn_prior && node_count > 0) {
       e->node_probabilities.Upload(unconditional_node_probabilities, node_count, e->stream);
@@ -954,6 +1466,7 @@ int sbnb_gp_create(int32_t taxon_count, int64_t pattern_count, const uint8_t* ti
     p.threshold = rescaling_threshold;
     p.log_threshold = std::log(rescaling_threshold);
     p.exchange = e->exchange.get();
+    p.matrix_cache = e->matrix_cache.get();
     p.status = e->status.get();
     ModelTables tables;
     BuildModelTables(ModelSpec::Parse("JC69", "constant", "none"), nullptr, &tables);
@@ -978,19 +1491,54 @@ int sbnb_gp_process_operations(sbnb_gp_engine* e, const int32_t* program, int64_
     Require(word_count >= 0 && (program != nullptr || word_count == 0), "NULL program.");
     if (word_count == 0) return;
     Bind(e);
-    ValidateProgram(e, program, word_count);
-    e->program.Upload(program, word_count, e->stream);
+    // The compiled form of a program seen before is still on the device.
+    CompiledProgram* compiled = nullptr;
+    for (auto& candidate : e->compiled)
+      if (candidate->source.size() == static_cast<size_t>(word_count) &&
+          std::memcmp(candidate->source.data(), program, word_count * sizeof(int32_t)) == 0)
+        compiled = candidate.get();
+    if (compiled == nullptr) {
+      ValidateProgram(GpShape{e->plv_count, e->gpcsp_count}, program, word_count);
+      if (e->compiled.size() >= kGpProgramCacheSize) {
+        auto oldest = std::min_element(e->compiled.begin(), e->compiled.end(),
+                                       [](const auto& a, const auto& b) { return a->last_used < b->last_used; });
+        SBNB_CUDA(cudaStreamSynchronize(e->stream));
+        e->compiled.erase(oldest);
+      }
+      e->compiled.push_back(std::make_unique<CompiledProgram>());
+      compiled = e->compiled.back().get();
+      CompileProgram(e->plv_count, e->gpcsp_count, program, word_count, compiled);
+      compiled->device.Upload(compiled->words.data(), compiled->words.size(), e->stream);
+    }
+    compiled->last_used = ++e->program_clock;
     SBNB_CUDA(cudaMemsetAsync(e->status.get(), 0, 2 * sizeof(int32_t), e->stream));
+    if (e->blocks > 1)  // (epochs restart at 1 in every launch)
+      SBNB_CUDA(cudaMemsetAsync(e->exchange.get(), 0,
+                                static_cast<size_t>(2) * e->blocks * 2 * kGpReduceValues * sizeof(double), e->stream));
     GpParams p = e->params;
-    p.program = e->program.get();
+    p.program = compiled->device.get();
     p.word_count = word_count;
     SBNB_CUDA(cudaEventRecord(e->begin, e->stream));
+    GpSmemPlan plan = e->plan;
+    if (plan.bytes + static_cast<size_t>(word_count) * sizeof(int32_t) <= kGpSmemBudget) {
+      plan.program_words = static_cast<int32_t>(word_count);
+      plan.bytes += static_cast<size_t>(word_count) * sizeof(int32_t);
+    }
+    // (multi-block launches were sized for the whole budget)
+    const size_t smem_bytes = e->blocks == 1 ? plan.bytes : kGpSmemBudget;
+    const bool single = static_cast<int64_t>(e->blocks) * e->threads >= e->pattern_count;
     if (e->blocks == 1) {
-      GpInterpretKernel<<<1, e->threads, 0, e->stream>>>(p);
+      if (single) {
+        GpInterpretKernel<true><<<1, e->threads, smem_bytes, e->stream>>>(p, plan);
+      } else {
+        GpInterpretKernel<false><<<1, e->threads, smem_bytes, e->stream>>>(p, plan);
+      }
     } else {
-      void* args[] = {&p};
-      SBNB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(GpInterpretKernel), dim3(e->blocks),
-                                            dim3(e->threads), args, 0, e->stream));
+      // (cooperative: every CTA resident at once, which the cross-CTA exchanges rely on)
+      void* args[] = {&p, &plan};
+      SBNB_CUDA(cudaLaunchCooperativeKernel(
+          single ? reinterpret_cast<void*>(GpInterpretKernel<true>) : reinterpret_cast<void*>(GpInterpretKernel<false>),
+          dim3(e->blocks), dim3(e->threads), args, smem_bytes, e->stream));
     }
     SBNB_CUDA(cudaGetLastError());
     SBNB_CUDA(cudaEventRecord(e->end, e->stream));
@@ -1003,7 +1551,39 @@ int sbnb_gp_process_operations(sbnb_gp_engine* e, const int32_t* program, int64_
     e->last_kernel_ms = ms;
     if (status[0] != kGpOk)
       Fail(status[0] == kGpFaultBadProgram ? SBNB_ERR_INVALID_ARGUMENT : SBNB_ERR_GP_ASSERT,
-           std::string(FaultMessage(status[0])) + " (operation at word " + std::to_string(status[1]) + ")");
+           std::string(FaultMessage(status[0])) + " (operation at word " + std::to_string(OriginalOffset(*compiled, status[1])) + ")");
+  });
+}
+
+int sbnb_gp_set_substitution_model(sbnb_gp_engine* e, const char* substitution, const double* params,
+                                   int32_t param_count) {
+  return Guard([&] {
+    Require(e != nullptr && substitution != nullptr, "NULL argument.");
+    const ModelSpec spec = ModelSpec::Parse(substitution, "constant", "none");
+    Require(param_count == spec.param_count,
+            std::string("The ") + substitution + " substitution model takes " + std::to_string(spec.param_count) +
+                " parameters.");
+    Require(params != nullptr || param_count == 0, "NULL parameters.");
+    ModelTables tables;
+    BuildModelTables(spec, params, &tables);
+    GpParams& p = e->params;
+    std::copy(tables.evec, tables.evec + 16, p.evec);
+    std::copy(tables.ivec, tables.ivec + 16, p.ivec);
+    std::copy(tables.eval, tables.eval + 4, p.eval);
+    std::copy(tables.freqs, tables.freqs + 4, p.freqs);
+  });
+}
+
+int sbnb_gp_schedule_program(int32_t plv_count, int32_t gpcsp_count, const int32_t* program, int64_t word_count,
+                             int32_t* out) {
+  return Guard([&] {
+    Require(plv_count >= 0 && gpcsp_count >= 0, "Negative PLV / GPCSP count.");
+    Require(word_count >= 0 && (program != nullptr || word_count == 0), "NULL program.");
+    Require(out != nullptr || word_count == 0, "NULL output.");
+    ValidateProgram(GpShape{plv_count, gpcsp_count}, program, word_count);
+    CompiledProgram compiled;
+    CompileProgram(plv_count, gpcsp_count, program, word_count, &compiled);
+    std::copy(compiled.words.begin(), compiled.words.end(), out);
   });
 }
 

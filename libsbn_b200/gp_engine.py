@@ -66,6 +66,16 @@ class GPOperations:
         return np.array(words, dtype=np.int32)
 
 
+def schedule_program(plv_count, gpcsp_count, program):
+    """The schedule the device runs for `program` (sbnb_gp_schedule_program; host only): the records
+    re-ordered by dependency level, the first record of a batch tagged with its length in bits 8+."""
+    program = np.ascontiguousarray(program, dtype=np.int32)
+    out = np.empty_like(program)
+    _capi.check(_capi.load().sbnb_gp_schedule_program(int(plv_count), int(gpcsp_count), _capi.as_int32_ptr(program),
+                                                      program.size, _capi.as_int32_ptr(out)))
+    return out
+
+
 def _tips(tips):
     """QuartetTipVector (quartet_hybrid_request.hpp): records (tip_node_id, plv_idx, gpcsp_idx)."""
     array = np.ascontiguousarray(np.array(tips, dtype=np.int32).reshape(-1, 3))
@@ -119,6 +129,13 @@ class GPEngine:
 
     def __del__(self):
         self.close()
+
+    def set_substitution_model(self, substitution, params=()):
+        """"JC69" (the reference's only GP model, gp_engine.hpp:143-154), "GTR" (6 rates + 4 frequencies) or
+        "HKY" (4 frequencies + kappa): an addition to the reference's interface."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        _capi.check(self._lib.sbnb_gp_set_substitution_model(self._handle, substitution.encode(),
+                                                             _capi.as_double_ptr(params), params.size))
 
     # ---- ProcessOperations (gp_engine.cpp:167-171)
     def process_operations(self, program):

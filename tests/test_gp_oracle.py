@@ -84,3 +84,99 @@ def test_asserts_surface():
     engine.rescaling_counts[3] = 2
     with pytest.raises(gp.GPAssertion, match="dest_ rescaling too large"):
         engine.process_operations([2, 3, 0, 0])
+
+
+# ---- the device's schedule of a program (sbnb_gp_schedule_program; host code of libsbn_b200.so)
+def _records(program):
+    """(kind, fields) per record; the batch length of word 0 (bits 8+) is dropped."""
+    size = {0: 2, 1: 3, 2: 4, 3: 4, 4: 4, 5: 4, 6: 3, 7: 1, 8: 4}
+    program = [int(w) for w in program]
+    pc, out = 0, []
+    while pc < len(program):
+        kind = program[pc] & 0xff
+        words = size[kind] if kind != 9 else 3 + program[pc + 2]
+        out.append((kind, tuple(program[pc + 1:pc + words]), program[pc] >> 8))
+        pc += words
+    return out
+
+
+@pytest.mark.parametrize("name,programs", [
+    ("ds1_dag", ["program_populate_plvs", "program_compute_likelihoods", "program_branch_length_optimization",
+                 "program_optimize_sbn_parameters", "program_marginal_likelihood"]),
+    ("five_taxon", ["program_populate_plvs", "program_branch_length_optimization"]),
+])
+def test_schedule_is_a_batched_permutation_of_the_program(name, programs):
+    from libsbn_b200.gp_engine import schedule_program
+    fx = load_fixture("gp_" + name)
+    for key in programs:
+        scheduled = schedule_program(fx["plv_count"], fx["gpcsp_count"], fx[key])
+        before, after = _records(fx[key]), _records(scheduled)
+        assert sorted((k, f) for k, f, _ in before) == sorted((k, f) for k, f, _ in after)
+        # batch lengths: a tagged record is followed by length - 1 untagged records of its kind
+        i = 0
+        while i < len(after):
+            kind, _, length = after[i]
+            assert length >= 1
+            assert all(after[i + j][0] == kind and after[i + j][2] == 0 for j in range(1, length))
+            i += length
+    populate = _records(schedule_program(fx["plv_count"], fx["gpcsp_count"], fx["program_populate_plvs"]))
+    assert sum(1 for _, _, length in populate if length >= 1) < len(populate) / 2  # most ops ride in batches
+
+
+@pytest.mark.parametrize("name", ["five_taxon", "hello_two_trees", "seven_taxon_all_trees", "five_taxon_threshold_0.5"])
+def test_scheduled_programs_compute_the_same_bits(name):
+    """Ops of one dependency level are independent: the re-ordered program run op by op on the
+    numpy oracle gives bit-identical PLVs, branch lengths, q and likelihoods."""
+    from libsbn_b200.gp_engine import schedule_program
+    fx = load_fixture("gp_" + name)
+    engines = [gp_cases.make_engine(factory, fx), gp_cases.make_engine(factory, fx)]
+    keys = ["program_populate_plvs", "program_compute_likelihoods", "program_branch_length_optimization",
+            "program_populate_plvs", "program_compute_likelihoods", "program_optimize_sbn_parameters"]
+    for key in keys:
+        if key not in fx:
+            continue
+        engines[0].process_operations(fx[key])
+        scheduled = schedule_program(fx["plv_count"], fx["gpcsp_count"], fx[key])
+        engines[1].process_operations(np.array([w & 0xff if i in _starts(scheduled) else w
+                                                for i, w in enumerate(scheduled)], dtype=np.int32))
+        assert np.array_equal(engines[0].plvs, engines[1].plvs)
+        assert np.array_equal(engines[0].branch_lengths, engines[1].branch_lengths)
+        assert np.array_equal(engines[0].q, engines[1].q)
+        assert np.array_equal(engines[0].rescaling_counts, engines[1].rescaling_counts)
+        assert np.array_equal(engines[0].log_likelihoods, engines[1].log_likelihoods, equal_nan=True)
+        assert np.array_equal(engines[0].log_marginal_likelihood, engines[1].log_marginal_likelihood)
+
+
+def _starts(program):
+    """Word offsets of the records' first words."""
+    size = {0: 2, 1: 3, 2: 4, 3: 4, 4: 4, 5: 4, 6: 3, 7: 1, 8: 4}
+    pc, out = 0, set()
+    while pc < len(program):
+        out.add(pc)
+        kind = int(program[pc]) & 0xff
+        pc += size[kind] if kind != 9 else 3 + int(program[pc + 2])
+    return out
+
+
+# ---- GP beyond JC69 (SURVEY.md 8f-4; not in the reference): pinned through a single-tree DAG
+GTR_PARAMS = np.array([0.05, 0.1, 0.15, 0.20, 0.25, 0.25, 0.1, 0.2, 0.3, 0.4])  # rooted_sbn_instance.hpp:336-337
+
+
+def test_gtr_marginal_of_a_single_tree_dag_is_the_tree_likelihood():
+    """data/hello_rooted.nwk = (jupiter,(mars,saturn)): with every branch at 0.1 the GP marginal of its
+    one-tree DAG is the likelihood of the unrooted star tree with the outgroup's edge at 0.2 -- computed
+    by the C restatement of the FatBeagle path (oracle/phylo.py, pinned to the reference's goldens)."""
+    from oracle import phylo
+    fx = load_fixture("gp_hello")
+    weights = fx["pattern_weights"]
+    for substitution, params in (("JC69", np.zeros(0)), ("GTR", GTR_PARAMS), ("HKY", np.array([0.1, 0.2, 0.3, 0.4, 2.0]))):
+        engine = gp_cases.make_engine(factory, fx)
+        engine.set_substitution_model(substitution, params)
+        engine.set_branch_lengths(np.full(int(fx["gpcsp_count"]), 0.1))
+        engine.process_operations(fx["program_populate_plvs"])
+        engine.process_operations(fx["program_compute_likelihoods"])
+        tree_params = params if substitution != "HKY" else np.concatenate([np.array([1, 2, 1, 1, 2, 1]) / 8, params[:4]])
+        want = phylo.log_likelihoods("JC69" if substitution == "JC69" else "GTR", "constant", fx["tip_states"], weights,
+                                     np.array([[3, 3, 3]]), np.array([[0.2, 0.1, 0.1, 0.0]]),
+                                     params=tree_params[None, :] if tree_params.size else None)[0]
+        assert abs(engine.get_log_marginal_likelihood() - want) < 1e-10 * abs(want), substitution
