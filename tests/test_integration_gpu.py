@@ -41,14 +41,14 @@ def _run_doctest(binary, *args):
     return done.returncode, tuple(int(x) for x in summary.groups()), failed_cases, text
 
 
-def _compare_with_reference_build(name, engine_cases, minimum_cases):
+def _compare_with_reference_build(name, engine_cases, minimum_cases, reference_name=None):
     """The suite built over libsbn_b200.so must pass every test case the UNMODIFIED
     reference build (oracle/_ref, BEAGLE-equivalent CPU kernels) passes on this very
     host, and every case that touches the likelihood engine.  (Some reference cases
     fail on their own: they hard-code libstdc++ hash-iteration orders or hold 23 EM
     iterations to 1e-12 across libm versions -- SURVEY.md 8c; none touches the engine.)"""
     ours = _artefact(name)
-    theirs = os.path.join(REF_RUN_DIR, name)
+    theirs = os.path.join(REF_RUN_DIR, reference_name or name)
     assert os.path.exists(theirs), theirs
     _, (total, passed, failed), our_failures, text = _run_doctest(ours)
     _, (ref_total, _, _), reference_failures, _ = _run_doctest(theirs)

@@ -1,0 +1,101 @@
+"""Partial-update HBM GB/s of the BEAGLE-compatible device library (libhmsbeagle_b200.so:
+libsbn_b200/csrc/beagle_shim.cu) -- SURVEY.md 8d's second metric, on the materialised
+op-at-a-time schedule where it is directly meaningful: one FatBeagle::BranchGradientInternals
+call sequence (fat_beagle.cpp:119-175) on a random tree at BASELINE configs[3] size (100 taxa x
+100k patterns x 4 categories, GTR), device time by CUDA events per BEAGLE call, bytes by
+SURVEY.md 8d's table (U = 32 C P per partial; compact tips and matrices ignored).
+
+    python tools/beagle_shim_bench.py [--taxa 100 --patterns 100000 --categories 4 --repeats 5]
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import test_beagle_shim as harness  # noqa: E402  (the BEAGLE call sequence of fat_beagle.cpp over ctypes)
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--taxa", type=int, default=100)
+    parser.add_argument("--patterns", type=int, default=100000)
+    parser.add_argument("--categories", type=int, default=4)
+    parser.add_argument("--repeats", type=int, default=5)
+    args = parser.parse_args()
+    n, P, C = args.taxa, args.patterns, args.categories
+    rng = np.random.default_rng(20261017)
+    states = rng.integers(0, 4, size=(n, P)).astype(np.int32)
+    states[rng.random(states.shape) < 0.01] = 4
+    post, pre = harness._random_tree_ops(n, rng, True)
+    lengths = np.maximum(rng.exponential(0.1, size=2 * n - 1), 1e-6)
+    evec, ivec, evals, freqs, q = harness._gtr()
+    rates = np.array([0.03, 0.25, 0.8, 2.92])[:C] if C == 4 else np.ones(C)
+    rates = rates / rates.mean()
+    beagle = harness.Beagle(harness.SHIM, n, P, C, True)
+    beagle.lib.sbnbBeagleLastKernelMs.restype = ctypes.c_double
+    beagle.set_tips(states, np.ones(P), True)
+    beagle.set_model(evec, ivec, evals, freqs, rates, np.full(C, 1.0 / C))
+    U = 32.0 * C * P
+    N = 2 * n - 1
+
+    def timed(call):
+        call()
+        return beagle.lib.sbnbBeagleLastKernelMs(beagle.handle)
+
+    derivative_args = [beagle._i(np.arange(N - 1)), beagle._i(np.arange(N - 1) + N), beagle._i(np.full(N - 1, N - 1)),
+                       beagle._i([0])]
+    sums = np.zeros(N - 1)
+
+    def derivatives():
+        beagle.ok(beagle.lib.beagleCalculateEdgeDerivatives(beagle.handle, *[a[1] for a in derivative_args], N - 1, None,
+                                                            sums.ctypes.data_as(harness._D), None))
+
+    keep_a, post_ptr = beagle._i(post)
+    keep_b, pre_ptr = beagle._i(pre)
+    results = {"post_ms": [], "pre_ms": [], "derivatives_ms": [], "call_sequence_ms": []}
+    for _ in range(args.repeats + 1):
+        t0 = time.perf_counter()
+        logl, sums, _, _ = beagle.log_likelihood_and_gradient(post, pre, lengths, q, rates, freqs, True)
+        results["call_sequence_ms"].append((time.perf_counter() - t0) * 1e3)
+        results["post_ms"].append(timed(lambda: beagle.ok(beagle.lib.beagleUpdatePartials(beagle.handle, post_ptr, len(post), 0))))
+        results["derivatives_ms"].append(timed(derivatives))
+        results["pre_ms"].append(timed(lambda: beagle.ok(beagle.lib.beagleUpdatePrePartials(beagle.handle, pre_ptr, len(pre), -1))))
+    med = {k: float(np.median(v[1:])) for k, v in results.items()}
+    # post-order writes n-1, reads n-2 partials; pre-order writes 2n-2, reads (2n-4) + (n-2)
+    post_bytes, pre_bytes = (2 * n - 3) * U, (5 * n - 8) * U
+    out = {
+        "workload": f"BEAGLE-compatible device library, one tree: {n} taxa x {P} patterns x {C} categories, GTR, rescaling on",
+        "partial_bytes_U": U,
+        "update_partials": {"ms": med["post_ms"], "algorithmic_GB": post_bytes / 1e9,
+                            "GBps": post_bytes / med["post_ms"] / 1e6},
+        "update_pre_partials": {"ms": med["pre_ms"], "algorithmic_GB": pre_bytes / 1e9,
+                                "GBps": pre_bytes / med["pre_ms"] / 1e6},
+        "edge_derivatives": {"ms": med["derivatives_ms"], "algorithmic_GB": (3 * n - 4) * U / 1e9,
+                             "GBps": (3 * n - 4) * U / med["derivatives_ms"] / 1e6},
+        "device_ms_per_logl_plus_gradient": med["post_ms"] + med["pre_ms"] + med["derivatives_ms"],
+        "branch_gradient_call_sequence_ms": med["call_sequence_ms"],
+        "note": "call_sequence includes the host <-> device copies of the BEAGLE API (per-site derivatives, a U-sized "
+                "root pre-order partial uploaded as fat_beagle.cpp:316-325 does) and a stream synchronisation per call",
+        "log_likelihood": logl,
+    }
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks):
+        hbm = json.load(open(peaks)).get("hbm_gbs")
+        if hbm:
+            out["hbm_peak_GBps_measured"] = hbm
+            out["update_partials"]["frac_of_peak"] = out["update_partials"]["GBps"] / hbm
+            out["update_pre_partials"]["frac_of_peak"] = out["update_pre_partials"]["GBps"] / hbm
+            out["edge_derivatives"]["frac_of_peak"] = out["edge_derivatives"]["GBps"] / hbm
+    beagle.close()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
