@@ -82,6 +82,18 @@ void sbnb_gp_destroy(sbnb_gp_engine* engine);
 int sbnb_gp_set_substitution_model(sbnb_gp_engine* engine, const char* substitution, const double* params,
                                    int32_t param_count);
 
+/*
+ * Rate categories (an addition, the reference's GPEngine has one rate): `site`
+ * and `params` as in the "entire site" block of a phylo_model_params row -- "constant",
+ * "weibull+K" (shape; the median discretisation of site_model.cpp:37-62) or "gamma+K" (shape),
+ * K = 1, 2, 4 or 8.  Every PLV becomes [pattern][category][4] (sbnb_gp_get_plv returns
+ * pattern_count * K * 4 doubles), every transition matrix P(r_c t) per category, every site
+ * likelihood the proportion-weighted sum over the categories; the op programs do not change.
+ * RESETS the PLVs and rescaling counts to their state after sbnb_gp_create.
+ */
+int sbnb_gp_set_site_model(sbnb_gp_engine* engine, const char* site, const double* params, int32_t param_count);
+int32_t sbnb_gp_category_count(const sbnb_gp_engine* engine);
+
 /* GPEngine::ProcessOperations (gp_engine.cpp:167-171): the whole program in one
  * kernel launch; returns after it has finished. */
 int sbnb_gp_process_operations(sbnb_gp_engine* engine, const int32_t* program, int64_t word_count);

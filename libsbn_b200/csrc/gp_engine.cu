@@ -76,7 +76,11 @@ enum GpFault : int {
 struct GpParams {
   int64_t pattern_count;
   int32_t plv_count, gpcsp_count;
-  double* plvs;             // [plv][pattern][4]
+  // rate categories (a power of two <= kGpMaxCategories; 1 = the reference's GPEngine): the
+  // lanes of a pattern's categories are adjacent, every PLV is [pattern][category][4]
+  int32_t categories, log2_categories;
+  double rates[8], proportions[8];
+  double* plvs;             // [plv][pattern][category][4]
   int32_t* counts;          // [block][warp][plv]  rescaling counts, one identical copy per warp
   double* branch_lengths;   // [gpcsp]
   double* q;                // [gpcsp]
@@ -169,6 +173,7 @@ __device__ __forceinline__ double LogAdd(double x, double y) {
 // mailboxes alternate with the epoch's parity: a CTA can post epoch r + 2 only after every
 // CTA has posted r + 1, i.e. after every CTA has read r.
 constexpr int kGpMaxGridBlocks = 160;
+constexpr int kGpMaxCategories = 8;
 #ifndef SBNB_GP_BATCH_OPS
 #define SBNB_GP_BATCH_OPS 2
 #endif
@@ -287,29 +292,31 @@ struct Reducer {
   __device__ void Barrier() { Sum(0.0); }
 };
 
-// One element of P(t) = V diag(exp(lambda t)) V^-1 per lane, computed by a half-warp:
-// lane (i, j) = ((lane >> 2) & 3, lane & 3) of either half returns P_ij.  The four
-// exponentials are computed once per half-warp (lanes 0..3 of the half) and exchanged by
-// shuffles -- the fp64 exp is ~45 instructions and a whole CTA shares one SM's fp64 pipe,
-// so the interpreter never lets every thread evaluate it redundantly.  Same operation
-// order per element as TransitionMatrix.
-__device__ __forceinline__ double HalfWarpTransitionElement(const GpParams& p, double t) {
-  const int lane = threadIdx.x & 31;
-  const double mine = exp(t * p.eval[lane & 3]);
-  const int i = (lane >> 2) & 3, j = lane & 3, base = lane & 16;
-  double sum = 0.0;
+// P_c(t) = V diag(exp(lambda r_c t)) V^-1 for every rate category c, computed by one warp into
+// out[c][16]: lane (c, k) = ((lane >> 2) % C, lane & 3) evaluates one exponential, the
+// elements are assembled from shuffles.  Same operation order per element as
+// TransitionMatrix (with one category, t r_0 = t exactly).
+__device__ __forceinline__ void WarpCategoryMatrices(const GpParams& p, double t, double* out) {
+  const int lane = threadIdx.x & 31, C = p.categories;
+  const double mine = exp((t * p.rates[(lane >> 2) & (C - 1)]) * p.eval[lane & 3]);
+  const int rounds = (16 * C + 31) / 32;
+  for (int r = 0; r < rounds; r++) {
+    const int idx = r * 32 + lane;
+    const int c = (idx >> 4) & (C - 1), i = (idx >> 2) & 3, j = idx & 3;
+    double sum = 0.0;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const double d = __shfl_sync(0xffffffffu, mine, base + k);
-    sum += (p.evec[i * 4 + k] * d) * p.ivec[k * 4 + j];
+    for (int k = 0; k < 4; k++) {
+      const double d = __shfl_sync(0xffffffffu, mine, c * 4 + k);
+      sum += (p.evec[i * 4 + k] * d) * p.ivec[k * 4 + j];
+    }
+    if (idx < 16 * C) out[idx] = sum;
   }
-  return sum;
 }
 
 // Shared-memory plan of the interpreter (dynamic; what does not fit stays in global memory).
 struct GpSmemPlan {
   int32_t program_words;  // the op program, staged once (0: read from global memory)
-  int32_t matrices;       // P(t_g) of every GPCSP + a copy of q: [gpcsp][16], [gpcsp]
+  int32_t matrices;       // P_c(t_g) of every GPCSP + a copy of q: [gpcsp][category][16], [gpcsp]
   int32_t counts;         // rescaling counts, one copy per warp: [warp][plv]
   int32_t scratch;        // doubles of UpdateSBNProbabilities scratch
   size_t bytes;
@@ -323,13 +330,13 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
   __shared__ unsigned long long reduce_smem[2][kGpMaxBlockThreads / 32][kGpReduceValues];
   __shared__ unsigned long long landed_smem[kGpMaxGridBlocks][kGpReduceValues];
   __shared__ int abort_flag;
-  __shared__ __align__(16) double warp_matrix_smem[kGpMaxBlockThreads / 32][16];
+  __shared__ __align__(16) double warp_matrix_smem[kGpMaxBlockThreads / 32][kGpMaxCategories * 16];
   if (threadIdx.x == 0) abort_flag = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = (blockDim.x + 31) >> 5;
-  const int G = p.gpcsp_count;
+  const int G = p.gpcsp_count, C = p.categories;
   // ---- carve-up: [matrices | q | scratch | counts | program]
   double* const matrices_smem = reinterpret_cast<double*>(gp_smem);
-  double* const q_smem = matrices_smem + (plan.matrices ? static_cast<size_t>(G) * 16 : 0);
+  double* const q_smem = matrices_smem + (plan.matrices ? static_cast<size_t>(G) * C * 16 : 0);
   double* const scratch = q_smem + (plan.matrices ? G : 0);
   int32_t* const counts_smem = reinterpret_cast<int32_t*>(scratch + plan.scratch);
   int32_t* const program_smem = counts_smem + (plan.counts ? static_cast<size_t>(warps) * p.plv_count : 0);
@@ -348,11 +355,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
   // ONE SM's fp64 pipe that was most of an op's 2 us.)
   double* const matrices = plan.matrices ? matrices_smem : p.matrix_cache;
   double* const q = plan.matrices ? q_smem : p.q;
-  for (int g0 = warp * 2; g0 < G; g0 += warps * 2) {
-    const int g = min(g0 + (lane >> 4), G - 1);  // (an odd tail: both halves compute the same matrix)
-    const double element = HalfWarpTransitionElement(p, p.branch_lengths[g]);
-    matrices[static_cast<size_t>(g) * 16 + (lane & 15)] = element;
-  }
+  for (int g = warp; g < G; g += warps) WarpCategoryMatrices(p, p.branch_lengths[g], matrices + static_cast<size_t>(g) * C * 16);
   if (plan.matrices)
     for (int g = threadIdx.x; g < G; g += blockDim.x) q_smem[g] = p.q[g];
   // Warps drift apart between reductions, so a shared copy of the rescaling
@@ -375,11 +378,22 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
 
   Reducer reduce{p, gridDim.x > 1, reduce_smem, landed_smem, &abort_flag};
   const int64_t P = p.pattern_count;
+  // A thread owns (pattern, category) pairs e = pattern * C + category: first, first + stride, ...
+  // (SINGLE: at most `first`).  Block sizes are multiples of 32 and C divides 32, so the
+  // category of a thread's pairs is always the same, and the C lanes of a pattern sit side
+  // by side in one warp.
+  const int64_t E = P << p.log2_categories;
   const int64_t first = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  // This thread's patterns: first, first + stride, ... (SINGLE: at most `first`).
-  const int64_t step = SINGLE ? P : stride;
-  auto plv = [&](int index) -> double* { return p.plvs + static_cast<size_t>(index) * P * 4; };
+  const int64_t step = SINGLE ? E : stride;
+  const int my_category = static_cast<int>(first) & (C - 1);
+  const double my_proportion = p.proportions[my_category];
+  // sum over the categories of a pattern (every lane of the warp takes part)
+  auto category_sum = [&](double value) -> double {
+    for (int m = 1; m < C; m <<= 1) value += __shfl_xor_sync(0xffffffffu, value, m);
+    return value;
+  };
+  auto plv = [&](int index) -> double* { return p.plvs + static_cast<size_t>(index) * E * 4; };
   auto fault = [&](int code, int64_t pc) {
     if (first == 0) {
       p.status[0] = code;
@@ -387,22 +401,20 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
     }
   };
   auto load_matrix = [&](int gpcsp, double (&m)[16]) {
-    const double2* src = reinterpret_cast<const double2*>(matrices + static_cast<size_t>(gpcsp) * 16);
+    const double2* src = reinterpret_cast<const double2*>(matrices + (static_cast<size_t>(gpcsp) * C + my_category) * 16);
 #pragma unroll
     for (int x = 0; x < 8; x++) {
       const double2 v = src[x];
       m[2 * x] = v.x, m[2 * x + 1] = v.y;
     }
   };
-  // P(t) for every lane of the warp: one element per lane of a half-warp, exchanged through
-  // the warp's 16 doubles of shared memory.
+  // P_c(t) of this lane's category, for every lane of the warp (through the warp's scratch).
   auto warp_transition_matrix = [&](double t, double (&m)[16]) {
-    const double element = HalfWarpTransitionElement(p, t);
     double* const mine = warp_matrix_smem[warp];
     __syncwarp();  // (the previous evaluation's reads)
-    if (lane < 16) mine[lane] = element;
+    WarpCategoryMatrices(p, t, mine);
     __syncwarp();
-    const double2* src = reinterpret_cast<const double2*>(mine);
+    const double2* src = reinterpret_cast<const double2*>(mine + my_category * 16);
 #pragma unroll
     for (int x = 0; x < 8; x++) {
       const double2 v = src[x];
@@ -416,11 +428,15 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
     double m[16];
     warp_transition_matrix(t, m);
     double local = 0.0;
-    for (int64_t k = first; k < P; k += stride) {
-      double r[4], l[4];
-      LoadState(rootward, k, r);
-      LoadState(leafward, k, l);
-      local = fma(p.weights[k], log(Bilinear(r, m, l)) + count_log, local);
+    for (int64_t base = first - lane; base < E; base += stride) {  // (warp-uniform: the category sum shuffles)
+      const int64_t e = base + lane;
+      double r[4] = {1.0, 1.0, 1.0, 1.0}, l[4] = {1.0, 1.0, 1.0, 1.0};
+      if (e < E) {
+        LoadState(rootward, e, r);
+        LoadState(leafward, e, l);
+      }
+      const double likelihood = category_sum(Bilinear(r, m, l) * my_proportion);
+      if (e < E && my_category == 0) local = fma(p.weights[e >> p.log2_categories], log(likelihood) + count_log, local);
     }
     return reduce.Sum(local);
   };
@@ -438,7 +454,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         const double zero[4] = {0.0, 0.0, 0.0, 0.0};
         for (int u = 0; u < batch; u++) {
           const int dest = program[pc + 2 * u + 1];
-          for (int64_t k = first; k < P; k += step) StoreState(plv(dest), k, zero);
+          for (int64_t k = first; k < E; k += step) StoreState(plv(dest), k, zero);
           set_count(dest, 0);
         }
         pc += 2 * batch;
@@ -449,7 +465,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
           const int dest = program[pc + 3 * u + 1], root = program[pc + 3 * u + 2];
           const double prior = q[root];
           const double x[4] = {prior * p.freqs[0], prior * p.freqs[1], prior * p.freqs[2], prior * p.freqs[3]};
-          for (int64_t k = first; k < P; k += step) StoreState(plv(dest), k, x);
+          for (int64_t k = first; k < E; k += step) StoreState(plv(dest), k, x);
           set_count(dest, 0);
         }
         pc += 3 * batch;
@@ -478,7 +494,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
           fault(kGpFaultDestRescaling, pc + 4 * faulty);
           return;
         }
-        for (int64_t k = first; k < P; k += step) {
+        for (int64_t k = first; k < E; k += step) {
           double s[kGpBatch][4], d[kGpBatch][4];
 #pragma unroll
           for (int u = 0; u < kGpBatch; u++) {
@@ -520,7 +536,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
             b_plv[u] = plv(program[pc + 4 * u + 3]);
           }
         }
-        for (int64_t k = first; k < P; k += step) {
+        for (int64_t k = first; k < E; k += step) {
           double a[kGpBatch][4], b[kGpBatch][4];
 #pragma unroll
           for (int u = 0; u < kGpBatch; u++) {
@@ -581,7 +597,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
                 rescaling++;
               }
               const double divisor = pow(p.threshold, static_cast<double>(rescaling));
-              for (int64_t k = first; k < P; k += step) {
+              for (int64_t k = first; k < E; k += step) {
                 double d[4];
                 LoadState(dest_plv[u], k, d);
 #pragma unroll
@@ -613,11 +629,15 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
                            static_cast<double>(counts[child]) * p.log_threshold;
           }
         }
-        for (int64_t k = first; k < P; k += step) {
+        for (int64_t base = first - lane; base < E; base += step) {  // (warp-uniform: the category sum shuffles)
+          const int64_t k = base + lane;
+          const bool on = k < E;
           double a[kGpBatch][4], b[kGpBatch][4];
 #pragma unroll
           for (int u = 0; u < kGpBatch; u++) {
-            if (u < batch) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[u][i] = b[u][i] = 1.0;
+            if (u < batch && on) {
               LoadState(parent_plv[u], k, a[u]);
               LoadState(child_plv[u], k, b[u]);
             }
@@ -627,7 +647,8 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
             if (u < batch) {
               double m[16];
               load_matrix(dest[u], m);
-              row[u][k] = log(Bilinear(a[u], m, b[u])) + count_log[u];
+              const double likelihood = category_sum(Bilinear(a[u], m, b[u]) * my_proportion);
+              if (on && my_category == 0) row[u][k >> p.log2_categories] = log(likelihood) + count_log[u];
               asm volatile("" ::: "memory");
             }
           }
@@ -646,7 +667,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         // down another path: a 7e-5 relative change in the sum of the branch lengths after six
         // sweeps; measured, and dropped for 12 % of the sweep's time).
         constexpr int kOwn = SINGLE ? 1 : 2;
-        const bool own_cover = P <= kOwn * stride;
+        const bool own_cover = E <= kOwn * stride;
         double r[kOwn][4], l[kOwn][4], weight[kOwn];
         if (own_cover) {
 #pragma unroll
@@ -655,10 +676,10 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
             weight[s] = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; i++) r[s][i] = l[s][i] = 1.0;  // (no pattern: log of a positive number x weight 0)
-            if (k < P) {
+            if (k < E) {
               LoadState(plv(rootward), k, r[s]);
               LoadState(plv(leafward), k, l[s]);
-              weight[s] = p.weights[k];
+              if (my_category == 0) weight[s] = p.weights[k >> p.log2_categories];
             }
           }
         }
@@ -669,7 +690,8 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
           warp_transition_matrix(t, m);
           double local = 0.0;
 #pragma unroll
-          for (int s = 0; s < kOwn; s++) local = fma(weight[s], log(Bilinear(r[s], m, l[s])) + count_log, local);
+          for (int s = 0; s < kOwn; s++)
+            local = fma(weight[s], log(category_sum(Bilinear(r[s], m, l[s]) * my_proportion)) + count_log, local);
           return -reduce.Sum(local);
         };
         const double current_log_branch_length = log(p.branch_lengths[gpcsp]);
@@ -744,11 +766,8 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         // (every warp has passed the last evaluation's barrier: nobody still reads the old values)
         const double new_length = (fx > current_value) ? exp(current_log_branch_length) : exp(x);
         p.branch_lengths[gpcsp] = new_length;
-        {
-          const double element = HalfWarpTransitionElement(p, new_length);
-          if (lane < 16) matrices[static_cast<size_t>(gpcsp) * 16 + lane] = element;
-          __syncwarp();
-        }
+        WarpCategoryMatrices(p, new_length, matrices + static_cast<size_t>(gpcsp) * C * 16);
+        __syncwarp();
         pc += 4;
         break;
       }
@@ -814,13 +833,20 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         const double count_log = static_cast<double>(counts[leafward]) * p.log_threshold;
         const double log_prior = log(q[rootsplit]);
         double* row = p.log_likelihoods + static_cast<size_t>(rootsplit) * P;
-        for (int64_t k = first; k < P; k += stride) {
-          double a[4], b[4];
-          LoadState(plv(stationary), k, a);
-          LoadState(plv(leafward), k, b);
-          const double value = log(fma(a[3], b[3], fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])))) + count_log;
-          p.log_marginal[k] = LogAdd(p.log_marginal[k], value);
-          row[k] = value - log_prior;
+        for (int64_t base = first - lane; base < E; base += stride) {  // (warp-uniform: the category sum shuffles)
+          const int64_t e = base + lane;
+          double a[4] = {1.0, 1.0, 1.0, 1.0}, b[4] = {1.0, 1.0, 1.0, 1.0};
+          if (e < E) {
+            LoadState(plv(stationary), e, a);
+            LoadState(plv(leafward), e, b);
+          }
+          const double site = category_sum(fma(a[3], b[3], fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0]))) * my_proportion);
+          if (e < E && my_category == 0) {
+            const int64_t k = e >> p.log2_categories;
+            const double value = log(site) + count_log;
+            p.log_marginal[k] = LogAdd(p.log_marginal[k], value);
+            row[k] = value - log_prior;
+          }
         }
         pc += 4;
         break;
@@ -858,25 +884,32 @@ __global__ void GpWeightedRowSumsKernel(const double* rows, const double* weight
   }
 }
 
-// LogLikelihoodAndDerivative (gp_engine.cpp:244-266), one block.
+// LogLikelihoodAndDerivative (gp_engine.cpp:244-266), one block.  With rate categories the site
+// likelihood is sum_c p_c r_c^T P(r_c t) l_c and its derivative in t sum_c p_c r_c r_c^T Q P(r_c t) l_c.
 __global__ void GpLogLikelihoodAndDerivativeKernel(const GpParams p, int leafward, int rootward, int gpcsp,
                                                    double* out) {
   __shared__ double smem[32][2];
   const int64_t P = p.pattern_count;
-  double m[16], dm[16];
+  const int C = p.categories;
   const double t = p.branch_lengths[gpcsp];
-  TransitionMatrix(p, t, false, m);
-  TransitionMatrix(p, t, true, dm);
   const double count_log = static_cast<double>(p.counts[rootward]) * p.log_threshold +
                            static_cast<double>(p.counts[leafward]) * p.log_threshold;
+  const double* rootward_plv = p.plvs + static_cast<size_t>(rootward) * P * C * 4;
+  const double* leafward_plv = p.plvs + static_cast<size_t>(leafward) * P * C * 4;
   double log_likelihood = 0.0, derivative = 0.0;
   for (int64_t k = threadIdx.x; k < P; k += blockDim.x) {
-    double r[4], l[4];
-    LoadState(p.plvs + static_cast<size_t>(rootward) * P * 4, k, r);
-    LoadState(p.plvs + static_cast<size_t>(leafward) * P * 4, k, l);
-    const double likelihood = Bilinear(r, m, l);
+    double likelihood = 0.0, slope = 0.0;
+    for (int c = 0; c < C; c++) {
+      double m[16], dm[16], r[4], l[4];
+      TransitionMatrix(p, t * p.rates[c], false, m);
+      TransitionMatrix(p, t * p.rates[c], true, dm);
+      LoadState(rootward_plv, k * C + c, r);
+      LoadState(leafward_plv, k * C + c, l);
+      likelihood += p.proportions[c] * Bilinear(r, m, l);
+      slope += p.proportions[c] * p.rates[c] * Bilinear(r, dm, l);
+    }
     log_likelihood = fma(p.weights[k], log(likelihood) + count_log, log_likelihood);
-    derivative = fma(p.weights[k], Bilinear(r, dm, l) / likelihood, derivative);
+    derivative = fma(p.weights[k], slope / likelihood, derivative);
   }
 #pragma unroll
   for (int s = 16; s >= 1; s >>= 1) {
@@ -930,34 +963,46 @@ __global__ void GpQuartetKernel(const GpParams p, const GpQuartetParams qp, doub
     if (threadIdx.x == 0) status[0] = 1;  // "Rescaling not implemented in CalculateQuartetHybridLikelihoods."
     return;
   }
+  const int C = p.categories;
   double m_rootward[16], m_sister[16], m_central[16], m_rotated[16], m_sorted[16];
-  TransitionMatrix(p, p.branch_lengths[rootward[2]], false, m_rootward);
-  TransitionMatrix(p, p.branch_lengths[sister[2]], false, m_sister);
-  TransitionMatrix(p, p.branch_lengths[qp.central_gpcsp], false, m_central);
-  TransitionMatrix(p, p.branch_lengths[rotated[2]], false, m_rotated);
-  TransitionMatrix(p, p.branch_lengths[sorted[2]], false, m_sorted);
+  auto matrices_of = [&](int c) {
+    const double rate = p.rates[c];
+    TransitionMatrix(p, p.branch_lengths[rootward[2]] * rate, false, m_rootward);
+    TransitionMatrix(p, p.branch_lengths[sister[2]] * rate, false, m_sister);
+    TransitionMatrix(p, p.branch_lengths[qp.central_gpcsp] * rate, false, m_central);
+    TransitionMatrix(p, p.branch_lengths[rotated[2]] * rate, false, m_rotated);
+    TransitionMatrix(p, p.branch_lengths[sorted[2]] * rate, false, m_sorted);
+  };
+  if (C == 1) matrices_of(0);
   auto apply = [](const double (&m)[16], const double (&x)[4], double (&y)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; i++)
       y[i] = fma(m[i * 4 + 3], x[3], fma(m[i * 4 + 2], x[2], fma(m[i * 4 + 1], x[1], m[i * 4] * x[0])));
   };
   const double log_rootward_tip_prior = log(qp.unconditional_node_probabilities[rootward[0]]);
+  const size_t plv_doubles = static_cast<size_t>(P) * C * 4;
   double local = 0.0;
   for (int64_t k = threadIdx.x; k < P; k += blockDim.x) {
-    double x[4], root_plv[4], y[4], r_s[4], q_s[4], r_sorted[4];
-    LoadState(p.plvs + static_cast<size_t>(rootward[1]) * P * 4, k, x);
-    apply(m_rootward, x, root_plv);
-    LoadState(p.plvs + static_cast<size_t>(sister[1]) * P * 4, k, x);
-    apply(m_sister, x, y);
+    double likelihood = 0.0;
+    for (int c = 0; c < C; c++) {
+      if (C > 1) matrices_of(c);  // (rate categories: not the reference's path; the matrices are per category)
+      const int64_t e = k * C + c;
+      double x[4], root_plv[4], y[4], r_s[4], q_s[4], r_sorted[4];
+      LoadState(p.plvs + rootward[1] * plv_doubles, e, x);
+      apply(m_rootward, x, root_plv);
+      LoadState(p.plvs + sister[1] * plv_doubles, e, x);
+      apply(m_sister, x, y);
 #pragma unroll
-    for (int i = 0; i < 4; i++) r_s[i] = root_plv[i] * y[i];
-    apply(m_central, r_s, q_s);
-    LoadState(p.plvs + static_cast<size_t>(rotated[1]) * P * 4, k, x);
-    apply(m_rotated, x, y);
+      for (int i = 0; i < 4; i++) r_s[i] = root_plv[i] * y[i];
+      apply(m_central, r_s, q_s);
+      LoadState(p.plvs + rotated[1] * plv_doubles, e, x);
+      apply(m_rotated, x, y);
 #pragma unroll
-    for (int i = 0; i < 4; i++) r_sorted[i] = q_s[i] * y[i];
-    LoadState(p.plvs + static_cast<size_t>(sorted[1]) * P * 4, k, x);
-    local = fma(p.weights[k], log(Bilinear(r_sorted, m_sorted, x)) - log_rootward_tip_prior, local);
+      for (int i = 0; i < 4; i++) r_sorted[i] = q_s[i] * y[i];
+      LoadState(p.plvs + sorted[1] * plv_doubles, e, x);
+      likelihood += p.proportions[c] * Bilinear(r_sorted, m_sorted, x);
+    }
+    local = fma(p.weights[k], log(likelihood) - log_rootward_tip_prior, local);
   }
 #pragma unroll
   for (int s = 16; s >= 1; s >>= 1) local += __shfl_xor_sync(0xffffffffu, local, s);
@@ -1029,6 +1074,7 @@ struct sbnb_gp_engine {
   DeviceArray<double> plvs, branch_lengths, q, hybrid, log_likelihoods, log_marginal, weights, exchange, scalars,
       node_probabilities, inverted_prior;
   DeviceArray<double> matrix_cache;
+  std::vector<uint8_t> host_tips;  // [taxon][pattern], for re-initialising the PLVs when the site model changes
   DeviceArray<int32_t> counts, program, status, tips;
   // programs seen before (the reference regenerates the same few schedules call after call)
   std::vector<std::unique_ptr<CompiledProgram>> compiled;
@@ -1049,6 +1095,7 @@ namespace {
 
 void CompileProgram(int32_t plv_count, int32_t gpcsp_count, const int32_t* program, int64_t word_count,
                     CompiledProgram* out);
+void SetCategories(sbnb_gp_engine* e, int categories, const double* rates, const double* proportions);
 
 void Bind(sbnb_gp_engine* e) { SBNB_CUDA(cudaSetDevice(e->device)); }
 
@@ -1202,6 +1249,95 @@ void QuartetLikelihoods(sbnb_gp_engine* e, int32_t central, const int32_t* rootw
   CopyOut(e, out->data(), e->scalars.get(), total);
   if (status[0] != 0)
     Fail(SBNB_ERR_GP_ASSERT, "Rescaling not implemented in CalculateQuartetHybridLikelihoods.");
+}
+
+// Everything that depends on the number of rate categories: the launch shape (one thread per
+// (pattern, category)), the shared-memory plan, the PLVs -- zeroed, tips re-initialised (one-hot /
+// all-ones gaps, gp_engine.cpp:268-286, the same in every category) -- and the rescaling counts.
+void SetCategories(sbnb_gp_engine* e, int categories, const double* rates, const double* proportions) {
+  Bind(e);
+  SBNB_CUDA(cudaStreamSynchronize(e->stream));
+  const int64_t P = e->pattern_count, E = P * categories;
+  const size_t gpcsps = std::max(e->gpcsp_count, 1);
+  // One (pattern, category) per thread while the resident CTAs can hold them (an op is then a
+  // short dependency chain per thread, and the CTAs share the fp64 work of the SMs they sit
+  // on); strided beyond that.
+  static const int forced_threads = EnvInt("SBNB_GP_THREADS", 0), forced_blocks = EnvInt("SBNB_GP_BLOCKS", 0);
+  const int max_blocks = std::min(kGpMaxGridBlocks, e->sm_count);
+  e->threads = E <= static_cast<int64_t>(kGpBlockThreads) * max_blocks
+                   ? static_cast<int>(std::min<int64_t>((E + 31) / 32 * 32, kGpBlockThreads))
+                   : kGpGridBlockThreads;
+  if (forced_threads > 0) e->threads = std::min(std::max(forced_threads / 32 * 32, 32), kGpMaxBlockThreads);
+  // Shared-memory plan, in the order of what an op touches most: the transition matrices
+  // (+ q), the per-warp rescaling counts, a scratch for UpdateSBNProbabilities; the op
+  // program takes what is left, launch by launch.
+  SBNB_CUDA(cudaFuncSetAttribute(GpInterpretKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(kGpSmemBudget)));
+  SBNB_CUDA(cudaFuncSetAttribute(GpInterpretKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(kGpSmemBudget)));
+  {
+    GpSmemPlan plan{};
+    size_t used = 0;
+    const size_t matrix_bytes = gpcsps * (16 * categories + 1) * sizeof(double);
+    plan.matrices = used + matrix_bytes <= kGpSmemBudget / 2;
+    if (plan.matrices) used += matrix_bytes;
+    plan.scratch = kGpScratchDoubles;
+    used += plan.scratch * sizeof(double);
+    const size_t count_bytes = static_cast<size_t>(e->threads / 32) * e->plv_count * sizeof(int32_t);
+    plan.counts = used + count_bytes <= kGpSmemBudget * 3 / 4;
+    if (plan.counts) used += count_bytes;
+    plan.bytes = used;
+    e->plan = plan;
+  }
+  {
+    int per_sm = 0;
+    SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, GpInterpretKernel<false>, e->threads, kGpSmemBudget));
+    const int64_t resident = std::min<int64_t>(static_cast<int64_t>(std::max(per_sm, 1)) * e->sm_count, max_blocks);
+    e->blocks = static_cast<int>(std::min<int64_t>((E + e->threads - 1) / e->threads, resident));
+    if (forced_blocks > 0) e->blocks = std::min(e->blocks, forced_blocks);
+  }
+  {
+    const size_t plv_doubles = static_cast<size_t>(e->plv_count) * E * 4;
+    e->plvs.Reserve(plv_doubles);
+    SBNB_CUDA(cudaMemsetAsync(e->plvs.get(), 0, plv_doubles * sizeof(double), e->stream));
+    std::vector<double> tips(static_cast<size_t>(e->taxon_count) * E * 4, 0.0);
+    for (int taxon = 0; taxon < e->taxon_count; taxon++)
+      for (int64_t k = 0; k < P; k++) {
+        const uint8_t symbol = e->host_tips[static_cast<size_t>(taxon) * P + k];
+        for (int c = 0; c < categories; c++) {
+          double* x = tips.data() + (static_cast<size_t>(taxon) * E + k * categories + c) * 4;
+          if (symbol == 4) {
+            x[0] = x[1] = x[2] = x[3] = 1.0;
+          } else if (symbol < 4) {
+            x[symbol] = 1.0;
+          }  // symbols > 4 leave the column zero, as the reference does
+        }
+      }
+    SBNB_CUDA(cudaMemcpyAsync(e->plvs.get(), tips.data(), tips.size() * sizeof(double), cudaMemcpyHostToDevice,
+                              e->stream));
+    SBNB_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  const size_t count_copies = static_cast<size_t>(e->blocks) * (kGpMaxBlockThreads / 32);
+  e->counts.Reserve(count_copies * e->plv_count);
+  SBNB_CUDA(cudaMemsetAsync(e->counts.get(), 0, count_copies * e->plv_count * sizeof(int32_t), e->stream));
+  e->exchange.Reserve(static_cast<size_t>(2) * e->blocks * 2 * kGpReduceValues);  // 8-byte words
+  e->matrix_cache.Reserve(gpcsps * 16 * categories);
+  SBNB_CUDA(cudaStreamSynchronize(e->stream));
+  GpParams& p = e->params;
+  p.pattern_count = P;
+  p.plv_count = e->plv_count;
+  p.gpcsp_count = e->gpcsp_count;
+  p.categories = categories;
+  p.log2_categories = 0;
+  while ((1 << p.log2_categories) < categories) p.log2_categories++;
+  for (int c = 0; c < kGpMaxCategories; c++) {
+    p.rates[c] = c < categories ? rates[c] : 1.0;
+    p.proportions[c] = c < categories ? proportions[c] : 0.0;
+  }
+  p.plvs = e->plvs.get();
+  p.counts = e->counts.get();
+  p.exchange = e->exchange.get();
+  p.matrix_cache = e->matrix_cache.get();
 }
 
 void CompileProgram(int32_t plv_count, int32_t gpcsp_count, const int32_t* program, int64_t word_count,
@@ -1370,62 +1506,9 @@ int sbnb_gp_create(int32_t taxon_count, int64_t pattern_count, const uint8_t* ti
     SBNB_CUDA(cudaEventCreate(&e->end));
     const int64_t P = pattern_count;
     const size_t gpcsps = std::max(gpcsp_count, 1);
-    // One site pattern per thread while the resident CTAs can hold them (an op is then a
-    // short dependency chain per thread, and the CTAs share the fp64 work of the SMs they
-    // sit on); strided patterns beyond that.
-    static const int forced_threads = EnvInt("SBNB_GP_THREADS", 0), forced_blocks = EnvInt("SBNB_GP_BLOCKS", 0);
-    const int max_blocks = std::min(kGpMaxGridBlocks, e->sm_count);
-    e->threads = P <= static_cast<int64_t>(kGpBlockThreads) * max_blocks
-                     ? static_cast<int>(std::min<int64_t>((P + 31) / 32 * 32, kGpBlockThreads))
-                     : kGpGridBlockThreads;
-    if (forced_threads > 0) e->threads = std::min(std::max(forced_threads / 32 * 32, 32), kGpMaxBlockThreads);
-    // Shared-memory plan, in the order of what an op touches most: the transition matrices
-    // (+ q), the per-warp rescaling counts, a scratch for UpdateSBNProbabilities; the op
-    // program takes what is left, launch by launch.
-    SBNB_CUDA(cudaFuncSetAttribute(GpInterpretKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(kGpSmemBudget)));
-    SBNB_CUDA(cudaFuncSetAttribute(GpInterpretKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(kGpSmemBudget)));
-    {
-      GpSmemPlan& plan = e->plan;
-      size_t used = 0;
-      const size_t matrix_bytes = gpcsps * 17 * sizeof(double);
-      plan.matrices = used + matrix_bytes <= kGpSmemBudget / 2;
-      if (plan.matrices) used += matrix_bytes;
-      plan.scratch = kGpScratchDoubles;
-      used += plan.scratch * sizeof(double);
-      const size_t count_bytes = static_cast<size_t>(e->threads / 32) * plv_count * sizeof(int32_t);
-      plan.counts = used + count_bytes <= kGpSmemBudget * 3 / 4;
-      if (plan.counts) used += count_bytes;
-      plan.bytes = used;
-    }
-    {
-      int per_sm = 0;
-      SBNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, GpInterpretKernel<false>, e->threads, kGpSmemBudget));
-      const int64_t resident = std::min<int64_t>(static_cast<int64_t>(std::max(per_sm, 1)) * e->sm_count, max_blocks);
-      e->blocks = static_cast<int>(std::min<int64_t>((P + e->threads - 1) / e->threads, resident));
-      if (forced_blocks > 0) e->blocks = std::min(e->blocks, forced_blocks);
-    }
-    // PLVs: zero, then one-hot tips / all-ones gaps (gp_engine.cpp:268-286).
-    {
-      const size_t plv_doubles = static_cast<size_t>(plv_count) * P * 4;
-      e->plvs.Reserve(plv_doubles);
-      SBNB_CUDA(cudaMemsetAsync(e->plvs.get(), 0, plv_doubles * sizeof(double), e->stream));
-      std::vector<double> tips(static_cast<size_t>(taxon_count) * P * 4, 0.0);
-      for (int taxon = 0; taxon < taxon_count; taxon++)
-        for (int64_t k = 0; k < P; k++) {
-          const uint8_t symbol = tip_states[static_cast<size_t>(taxon) * P + k];
-          double* x = tips.data() + (static_cast<size_t>(taxon) * P + k) * 4;
-          if (symbol == 4) {
-            x[0] = x[1] = x[2] = x[3] = 1.0;
-          } else if (symbol < 4) {
-            x[symbol] = 1.0;
-          }  // symbols > 4 leave the column zero, as the reference does
-        }
-      SBNB_CUDA(cudaMemcpyAsync(e->plvs.get(), tips.data(), tips.size() * sizeof(double), cudaMemcpyHostToDevice,
-                                e->stream));
-      SBNB_CUDA(cudaStreamSynchronize(e->stream));
-    }
+    e->host_tips.assign(tip_states, tip_states + static_cast<size_t>(taxon_count) * P);
+    const double unit = 1.0;
+    SetCategories(e.get(), 1, &unit, &unit);
     e->weights.Upload(pattern_weights, P, e->stream);
     std::vector<double> branch_lengths(gpcsps, 0.1);  // default_branch_length_, gp_engine.hpp:84
     e->branch_lengths.Upload(branch_lengths.data(), gpcsps, e->stream);
@@ -1437,11 +1520,6 @@ int sbnb_gp_create(int32_t taxon_count, int64_t pattern_count, const uint8_t* ti
     e->log_marginal.Upload(minus_infinity.data(), P, e->stream);
     e->log_likelihoods.Reserve(gpcsps * P);
     SBNB_CUDA(cudaMemsetAsync(e->log_likelihoods.get(), 0, gpcsps * P * sizeof(double), e->stream));
-    const size_t count_copies = static_cast<size_t>(e->blocks) * (kGpMaxBlockThreads / 32);
-    e->counts.Reserve(count_copies * plv_count);
-    SBNB_CUDA(cudaMemsetAsync(e->counts.get(), 0, count_copies * plv_count * sizeof(int32_t), e->stream));
-    e->exchange.Reserve(static_cast<size_t>(2) * e->blocks * 2 * kGpReduceValues);  // 8-byte words
-    e->matrix_cache.Reserve(gpcsps * 16);
     e->status.Reserve(2);
     if (unconditional_node_probabilities && inverted_sbn_prior && node_count > 0) {
       e->node_probabilities.Upload(unconditional_node_probabilities, node_count, e->stream);
@@ -1452,11 +1530,6 @@ int sbnb_gp_create(int32_t taxon_count, int64_t pattern_count, const uint8_t* ti
     SBNB_CUDA(cudaStreamSynchronize(e->stream));
 
     GpParams& p = e->params;
-    p.pattern_count = P;
-    p.plv_count = plv_count;
-    p.gpcsp_count = gpcsp_count;
-    p.plvs = e->plvs.get();
-    p.counts = e->counts.get();
     p.branch_lengths = e->branch_lengths.get();
     p.q = e->q.get();
     p.hybrid = e->hybrid.get();
@@ -1465,8 +1538,6 @@ int sbnb_gp_create(int32_t taxon_count, int64_t pattern_count, const uint8_t* ti
     p.weights = e->weights.get();
     p.threshold = rescaling_threshold;
     p.log_threshold = std::log(rescaling_threshold);
-    p.exchange = e->exchange.get();
-    p.matrix_cache = e->matrix_cache.get();
     p.status = e->status.get();
     ModelTables tables;
     BuildModelTables(ModelSpec::Parse("JC69", "constant", "none"), nullptr, &tables);
@@ -1526,7 +1597,7 @@ int sbnb_gp_process_operations(sbnb_gp_engine* e, const int32_t* program, int64_
     }
     // (multi-block launches were sized for the whole budget)
     const size_t smem_bytes = e->blocks == 1 ? plan.bytes : kGpSmemBudget;
-    const bool single = static_cast<int64_t>(e->blocks) * e->threads >= e->pattern_count;
+    const bool single = static_cast<int64_t>(e->blocks) * e->threads >= e->pattern_count * e->params.categories;
     if (e->blocks == 1) {
       if (single) {
         GpInterpretKernel<true><<<1, e->threads, smem_bytes, e->stream>>>(p, plan);
@@ -1573,6 +1644,24 @@ int sbnb_gp_set_substitution_model(sbnb_gp_engine* e, const char* substitution, 
     std::copy(tables.freqs, tables.freqs + 4, p.freqs);
   });
 }
+
+int sbnb_gp_set_site_model(sbnb_gp_engine* e, const char* site, const double* params, int32_t param_count) {
+  return Guard([&] {
+    Require(e != nullptr && site != nullptr, "NULL argument.");
+    const ModelSpec spec = ModelSpec::Parse("JC69", site, "none");
+    Require(param_count == spec.param_count,
+            std::string("The ") + site + " site model takes " + std::to_string(spec.param_count) + " parameters.");
+    Require(params != nullptr || param_count == 0, "NULL parameters.");
+    const int C = spec.category_count;
+    Require(C >= 1 && C <= kGpMaxCategories && (C & (C - 1)) == 0,
+            "The GP engine takes 1, 2, 4 or 8 rate categories.");
+    ModelTables tables;
+    BuildSite(spec, params, &tables);
+    SetCategories(e, C, tables.rates, tables.weights);
+  });
+}
+
+int32_t sbnb_gp_category_count(const sbnb_gp_engine* e) { return e ? e->params.categories : 0; }
 
 int sbnb_gp_schedule_program(int32_t plv_count, int32_t gpcsp_count, const int32_t* program, int64_t word_count,
                              int32_t* out) {
@@ -1774,7 +1863,8 @@ int sbnb_gp_get_plv(sbnb_gp_engine* e, int32_t plv_idx, double* out) {
     Require(e && out, "NULL argument.");
     CheckPlv(e, plv_idx);
     Bind(e);
-    CopyOut(e, out, e->plvs.get() + static_cast<size_t>(plv_idx) * e->pattern_count * 4, e->pattern_count * 4);
+    const size_t plv_doubles = static_cast<size_t>(e->pattern_count) * e->params.categories * 4;
+    CopyOut(e, out, e->plvs.get() + plv_idx * plv_doubles, plv_doubles);
   });
 }
 

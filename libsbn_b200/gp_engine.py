@@ -137,6 +137,17 @@ class GPEngine:
         _capi.check(self._lib.sbnb_gp_set_substitution_model(self._handle, substitution.encode(),
                                                              _capi.as_double_ptr(params), params.size))
 
+    def set_site_model(self, site, params=()):
+        """"constant", "weibull+K" or "gamma+K" (K = 1, 2, 4, 8) rate categories: an addition to the
+        reference's interface.  Resets the PLVs; get_plv then returns [pattern][K * 4]."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        _capi.check(self._lib.sbnb_gp_set_site_model(self._handle, site.encode(), _capi.as_double_ptr(params),
+                                                     params.size))
+
+    @property
+    def category_count(self):
+        return int(self._lib.sbnb_gp_category_count(self._handle))
+
     # ---- ProcessOperations (gp_engine.cpp:167-171)
     def process_operations(self, program):
         program = np.ascontiguousarray(program, dtype=np.int32)
@@ -228,9 +239,10 @@ class GPEngine:
 
     # ---- diagnostics
     def get_plv(self, plv_idx):
-        out = np.empty(self.pattern_count * 4, dtype=np.float64)
+        width = 4 * self.category_count
+        out = np.empty(self.pattern_count * width, dtype=np.float64)
         _capi.check(self._lib.sbnb_gp_get_plv(self._handle, int(plv_idx), _capi.as_double_ptr(out)))
-        return out.reshape(self.pattern_count, 4)
+        return out.reshape(self.pattern_count, width)
 
     def get_rescaling_counts(self):
         out = np.empty(self.plv_count, dtype=np.int32)

@@ -180,3 +180,20 @@ def test_gtr_marginal_of_a_single_tree_dag_is_the_tree_likelihood():
                                      np.array([[3, 3, 3]]), np.array([[0.2, 0.1, 0.1, 0.0]]),
                                      params=tree_params[None, :] if tree_params.size else None)[0]
         assert abs(engine.get_log_marginal_likelihood() - want) < 1e-10 * abs(want), substitution
+
+
+def test_rate_categories_on_a_single_tree_dag_are_the_tree_likelihood():
+    """The same pin for rate categories in the GP engine (not in the reference): GTR + weibull+4 on
+    the one-tree DAG equals FatBeagle's GTR + weibull+4 log likelihood of the tree."""
+    from oracle import phylo
+    fx = load_fixture("gp_hello")
+    for site, shape in (("weibull+4", 0.5), ("weibull+2", 1.3)):
+        engine = gp_cases.make_engine(factory, fx)
+        engine.set_substitution_model("GTR", GTR_PARAMS)
+        engine.set_site_model(site, [shape])
+        engine.set_branch_lengths(np.full(int(fx["gpcsp_count"]), 0.1))
+        engine.process_operations(fx["program_populate_plvs"])
+        engine.process_operations(fx["program_compute_likelihoods"])
+        want = phylo.log_likelihoods("GTR", site, fx["tip_states"], fx["pattern_weights"], np.array([[3, 3, 3]]),
+                                     np.array([[0.2, 0.1, 0.1, 0.0]]), params=np.concatenate([GTR_PARAMS, [shape]])[None, :])[0]
+        assert abs(engine.get_log_marginal_likelihood() - want) < 1e-10 * abs(want), site
