@@ -33,6 +33,13 @@ all 2n-2 branch-length derivatives, i.e. one BranchGradientInternals-equivalent
   small_problem : BASELINE.json configs[0..1] -- DS1 (27 taxa x 934 patterns) x 100
              topologies: call latency of JC69 log_likelihoods and of the full GTR+weibull4
              phylo_gradients at 10 and 100 trees, beside the CPU oracle port on all cores.
+  partial_update : BASELINE.json's second metric -- partial-update HBM GB/s against the measured
+             peak -- on the op-at-a-time schedule where it is directly meaningful: the
+             BEAGLE-compatible device library (libhmsbeagle_b200.so, the inner boundary) running
+             FatBeagle's call sequence for one tree at the headline size, bytes by SURVEY.md 8d.
+  gp       : BASELINE.json configs[2] -- generalized pruning on the DS1 subsplit DAG: device time
+             of each op program of the reference's schedule, and the unmodified python
+             `gp_instance` over this library beside the reference's own Eigen code on the host.
   cpu_baseline / --impl reference: the UNMODIFIED reference host code (oracle/_ref, its
              own python module, thread pool = host cores) over the BEAGLE-equivalent CPU
              kernels of oracle/beagle_cpu.cpp, at the FULL pattern count on one tree per
@@ -427,6 +434,24 @@ def small_problem_leg(local_rank):
     return out
 
 
+def partial_update_leg(local_rank):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import beagle_shim_bench
+    return beagle_shim_bench.measure(device=local_rank)
+
+
+def gp_leg(local_rank):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gp_bench
+    import gp_kernel_time
+    out = {"device_ms_per_program": gp_kernel_time.measure(device=local_rank)}
+    try:
+        out["python_gp_instance"] = gp_bench.measure(repeats=5, iterations=5)
+    except (OSError, RuntimeError, subprocess.SubprocessError, ValueError) as error:  # (artefacts not built)
+        out["python_gp_instance"] = {"unavailable": str(error)[:200]}
+    return out
+
+
 # --------------------------------------------------------------------------- our arm
 
 def run_ours(args):
@@ -618,6 +643,10 @@ def run_ours(args):
         # ---- BASELINE configs[0..1]: the small-problem regime (one GPU) ----------------
         if world == 1:
             line["small_problem"] = small_problem_leg(local_rank)
+            # ---- BASELINE's second metric on the materialised (BEAGLE-compatible) schedule,
+            #      and configs[2]: generalized pruning on the DS1 DAG ----------------------
+            line["partial_update"] = partial_update_leg(local_rank)
+            line["gp"] = gp_leg(local_rank)
 
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         sample_trees = reference_trees(args)

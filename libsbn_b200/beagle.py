@@ -1,0 +1,129 @@
+"""ctypes binding of the inner boundary: include/libhmsbeagle/beagle.h as implemented on the device by
+libsbn_b200/lib/libhmsbeagle_b200.so (libsbn_b200/csrc/beagle_shim.cu), driven with the call sequence the
+reference's FatBeagle makes (src/fat_beagle.cpp:50-70, 119-175, 207-362).  The same class runs over any
+other library with the same ABI (the tests pass the CPU restatement's path to compare call by call)."""
+import ctypes
+import os
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmsbeagle_b200.so")
+OP_NONE = -1
+_I, _D = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+
+
+class Beagle:
+    """The BEAGLE calls of fat_beagle.cpp over one of the two libraries."""
+
+    def __init__(self, path, n, P, C, use_tip_states):
+        self.lib = ctypes.CDLL(path or LIB_PATH)
+        self.n, self.P, self.C, self.N = n, P, C, 2 * n - 1
+        partials = 3 * n - 2 + (0 if use_tip_states else n)  # fat_beagle.cpp:207-256
+        self.handle = self.lib.beagleCreateInstance(n, partials, n if use_tip_states else 0, 4, P, 1, 2 * self.N, C,
+                                                    partials + 1, None, 0, 0, 1 << 6, None)
+        assert self.handle >= 0, self.handle
+
+    def ok(self, code):
+        assert code == 0, code
+
+    def _d(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return a, a.ctypes.data_as(_D)
+
+    def _i(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        return a, a.ctypes.data_as(_I)
+
+    def set_tips(self, states, weights, use_tip_states):
+        for tip in range(self.n):
+            if use_tip_states:
+                keep, ptr = self._i(states[tip])
+                self.ok(self.lib.beagleSetTipStates(self.handle, tip, ptr))
+            else:
+                partial = np.zeros((self.P, 4))
+                for k, s in enumerate(states[tip]):
+                    partial[k, :] = 1.0 if s >= 4 else 0.0
+                    if s < 4:
+                        partial[k, s] = 1.0
+                keep, ptr = self._d(partial)
+                self.ok(self.lib.beagleSetTipPartials(self.handle, tip, ptr))
+        keep, ptr = self._d(weights)
+        self.ok(self.lib.beagleSetPatternWeights(self.handle, ptr))
+
+    def set_model(self, evec, ivec, evals, freqs, rates, proportions):
+        keeps = [self._d(x) for x in (evec, ivec, evals, freqs, rates, proportions)]
+        self.ok(self.lib.beagleSetStateFrequencies(self.handle, 0, keeps[3][1]))
+        self.ok(self.lib.beagleSetEigenDecomposition(self.handle, 0, keeps[0][1], keeps[1][1], keeps[2][1]))
+        self.ok(self.lib.beagleSetCategoryWeights(self.handle, 0, keeps[5][1]))
+        self.ok(self.lib.beagleSetCategoryRates(self.handle, keeps[4][1]))
+
+    def log_likelihood_and_gradient(self, post_ops, pre_ops, lengths, q, rates, freqs, rescaling):
+        """FatBeagle::BranchGradientInternals (fat_beagle.cpp:119-175)."""
+        n, N = self.n, self.N
+        keep_i, idx = self._i(np.arange(N - 1))
+        keep_l, lens = self._d(lengths[:N - 1])
+        self.ok(self.lib.beagleUpdateTransitionMatrices(self.handle, 0, idx, None, None, lens, N - 1))
+        dq = np.stack([r * q for r in rates])
+        keep_q, dq_ptr = self._d(dq)
+        self.ok(self.lib.beagleSetDifferentialMatrix(self.handle, N - 1, dq_ptr))
+        cumulative = 0 if rescaling else OP_NONE
+        if rescaling:
+            self.ok(self.lib.beagleResetScaleFactors(self.handle, 0))
+        keep_a, ops = self._i(post_ops)
+        self.ok(self.lib.beagleUpdatePartials(self.handle, ops, len(post_ops), cumulative))
+        root_pre = np.tile(freqs, self.C * self.P)
+        keep_r, root_ptr = self._d(root_pre)
+        self.ok(self.lib.beagleSetPartials(self.handle, 2 * N - 1, root_ptr))
+        keep_b, ops = self._i(pre_ops)
+        self.ok(self.lib.beagleUpdatePrePartials(self.handle, ops, len(pre_ops), OP_NONE))
+        keep_1, post_idx = self._i(np.arange(N - 1))
+        keep_2, pre_idx = self._i(np.arange(N - 1) + N)
+        keep_3, dm_idx = self._i(np.full(N - 1, N - 1))
+        keep_4, zero = self._i([0])
+        sums, squares = np.zeros(N - 1), np.zeros(N - 1)
+        per_site = np.zeros((N - 1, self.P))
+        self.ok(self.lib.beagleCalculateEdgeDerivatives(self.handle, post_idx, pre_idx, dm_idx, zero, N - 1,
+                                                        per_site.ctypes.data_as(_D), sums.ctypes.data_as(_D),
+                                                        squares.ctypes.data_as(_D)))
+        keep_5, root = self._i([N - 1])
+        keep_6, cum = self._i([cumulative])
+        logl = ctypes.c_double()
+        self.ok(self.lib.beagleCalculateRootLogLikelihoods(self.handle, root, zero, zero, cum, 1, ctypes.byref(logl)))
+        return logl.value, sums, squares, per_site
+
+    def close(self):
+        self.ok(self.lib.beagleFinalizeInstance(self.handle))
+
+
+def random_tree_operations(n, rng, rescaling):
+    """A random rooted binary tree in libsbn's numbering (leaves 0..n-1, internal nodes in post-order,
+    root 2n-2) as the op lists of fat_beagle.cpp:327-362."""
+    N = 2 * n - 1
+    roots, children, next_id = list(range(n)), {}, n
+    while len(roots) > 1:
+        a, b = (roots.pop(int(rng.integers(len(roots)))) for _ in range(2))
+        children[next_id] = (a, b)
+        roots.append(next_id)
+        next_id += 1
+    post = [[v, (v - n + 1) if rescaling else OP_NONE, OP_NONE, a, a, b, b] for v, (a, b) in sorted(children.items())]
+    pre = []
+    for v in sorted(children, reverse=True):  # parents before children
+        for child, sister in (children[v], children[v][::-1]):
+            pre.append([child + N, (child + 1 + n - 1) if rescaling else OP_NONE, OP_NONE, v + N, child, sister, sister])
+    return np.array(post, dtype=np.int32), np.array(pre, dtype=np.int32)
+
+
+def gtr_eigensystem():
+    rates = np.array([0.05, 0.1, 0.15, 0.20, 0.25, 0.25])
+    freqs = np.array([0.1, 0.2, 0.3, 0.4])
+    q = np.zeros((4, 4))
+    index = 0
+    for i in range(4):
+        for j in range(i + 1, 4):
+            q[i, j], q[j, i] = rates[index] * freqs[j], rates[index] * freqs[i]
+            index += 1
+    q -= np.diag(q.sum(axis=1))
+    q /= -np.sum(np.diag(q) * freqs)
+    root = np.sqrt(freqs)
+    values, vectors = np.linalg.eigh(root[:, None] * q / root[None, :])
+    return vectors / root[:, None], vectors.T * root[None, :], values, freqs, q

@@ -18,27 +18,21 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-import test_beagle_shim as harness  # noqa: E402  (the BEAGLE call sequence of fat_beagle.cpp over ctypes)
+from libsbn_b200 import beagle as harness  # noqa: E402  (the BEAGLE call sequence of fat_beagle.cpp over ctypes)
 
 
-def main():
-    parser = argparse.ArgumentParser()
-    parser.add_argument("--taxa", type=int, default=100)
-    parser.add_argument("--patterns", type=int, default=100000)
-    parser.add_argument("--categories", type=int, default=4)
-    parser.add_argument("--repeats", type=int, default=5)
-    args = parser.parse_args()
-    n, P, C = args.taxa, args.patterns, args.categories
+def measure(n=100, P=100000, C=4, repeats=5, device=None):
+    if device is not None:
+        os.environ["SBNB_BEAGLE_DEVICE"] = str(device)
     rng = np.random.default_rng(20261017)
     states = rng.integers(0, 4, size=(n, P)).astype(np.int32)
     states[rng.random(states.shape) < 0.01] = 4
-    post, pre = harness._random_tree_ops(n, rng, True)
+    post, pre = harness.random_tree_operations(n, rng, True)
     lengths = np.maximum(rng.exponential(0.1, size=2 * n - 1), 1e-6)
-    evec, ivec, evals, freqs, q = harness._gtr()
+    evec, ivec, evals, freqs, q = harness.gtr_eigensystem()
     rates = np.array([0.03, 0.25, 0.8, 2.92])[:C] if C == 4 else np.ones(C)
     rates = rates / rates.mean()
-    beagle = harness.Beagle(harness.SHIM, n, P, C, True)
+    beagle = harness.Beagle(None, n, P, C, True)
     beagle.lib.sbnbBeagleLastKernelMs.restype = ctypes.c_double
     beagle.set_tips(states, np.ones(P), True)
     beagle.set_model(evec, ivec, evals, freqs, rates, np.full(C, 1.0 / C))
@@ -60,7 +54,7 @@ def main():
     keep_a, post_ptr = beagle._i(post)
     keep_b, pre_ptr = beagle._i(pre)
     results = {"post_ms": [], "pre_ms": [], "derivatives_ms": [], "call_sequence_ms": []}
-    for _ in range(args.repeats + 1):
+    for _ in range(repeats + 1):
         t0 = time.perf_counter()
         logl, sums, _, _ = beagle.log_likelihood_and_gradient(post, pre, lengths, q, rates, freqs, True)
         results["call_sequence_ms"].append((time.perf_counter() - t0) * 1e3)
@@ -94,7 +88,17 @@ def main():
             out["update_pre_partials"]["frac_of_peak"] = out["update_pre_partials"]["GBps"] / hbm
             out["edge_derivatives"]["frac_of_peak"] = out["edge_derivatives"]["GBps"] / hbm
     beagle.close()
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--taxa", type=int, default=100)
+    parser.add_argument("--patterns", type=int, default=100000)
+    parser.add_argument("--categories", type=int, default=4)
+    parser.add_argument("--repeats", type=int, default=5)
+    args = parser.parse_args()
+    print(json.dumps(measure(args.taxa, args.patterns, args.categories, args.repeats)))
 
 
 if __name__ == "__main__":

@@ -98,32 +98,38 @@ def run_arm(arm, newick, repeats, iterations):
     return result
 
 
-def main():
-    parser = argparse.ArgumentParser()
-    parser.add_argument("--repeats", type=int, default=5)
-    parser.add_argument("--iterations", type=int, default=5)
-    parser.add_argument("--arms", default="reference,ours")
-    args = parser.parse_args()
+def measure(repeats=5, iterations=5, arms=("reference", "ours")):
     source = os.path.join(RUN_DIR, "data", "DS1.100_topologies.nwk")
+    if not os.path.exists(source):
+        raise RuntimeError(f"{source} missing (staged by make -C oracle ref)")
     with tempfile.TemporaryDirectory() as scratch:
         newick = os.path.join(scratch, "ds1_100_rooted.nwk")
         with open(source) as handle, open(newick, "w") as out:
             for line in handle:
                 if line.strip():
                     out.write(root_newick(line) + "\n")
-        results = {}
-        for arm in args.arms.split(","):
-            results[arm] = run_arm(arm, newick, args.repeats, args.iterations)
-            print(json.dumps(results[arm]))
+        results = {arm: run_arm(arm, newick, repeats, iterations) for arm in arms}
     if all("plv_sweep_s" in results.get(arm, {}) for arm in ("reference", "ours")):
         ref, ours = results["reference"], results["ours"]
-        print(json.dumps({
+        results["summary"] = {
             "workload": "GP on the DS1 subsplit DAG (27 taxa, 934 patterns, 100 rooted topologies)",
             "plv_sweep_speedup": ref["plv_sweep_s"] / ours["plv_sweep_s"],
             "estimate_branch_lengths_speedup": ref["estimate_branch_lengths_s"] / ours["estimate_branch_lengths_s"],
             "branch_length_sum_rel_diff": abs(ref["branch_length_sum"] - ours["branch_length_sum"]) /
             abs(ref["branch_length_sum"]),
-            "cpu_cores_used_by_reference": 1}))
+            "cpu_cores_used_by_reference": 1}
+    return results
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--repeats", type=int, default=5)
+    parser.add_argument("--iterations", type=int, default=5)
+    parser.add_argument("--arms", default="reference,ours")
+    args = parser.parse_args()
+    results = measure(args.repeats, args.iterations, tuple(args.arms.split(",")))
+    for value in results.values():
+        print(json.dumps(value))
 
 
 if __name__ == "__main__":

@@ -20,24 +20,21 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from libsbn_b200.gp_engine import GPEngine  # noqa: E402
 
 
-def main():
-    parser = argparse.ArgumentParser()
-    parser.add_argument("--repeats", type=int, default=20)
-    args = parser.parse_args()
+def measure(repeats=20, device=0):
     fx = dict(np.load(os.path.join(ROOT, "tests", "golden", "gp_ds1_dag.npz")))
     engine = GPEngine(fx["tip_states"], fx["pattern_weights"], int(fx["site_count"]), int(fx["plv_count"]),
                       int(fx["gpcsp_count"]), rescaling_threshold=float(fx["rescaling_threshold"]),
                       sbn_prior=fx["sbn_prior"],
                       unconditional_node_probabilities=fx["unconditional_node_probabilities"],
-                      inverted_sbn_prior=fx["inverted_sbn_prior"])
+                      inverted_sbn_prior=fx["inverted_sbn_prior"], device=device)
     engine.set_branch_lengths(fx["initial_branch_lengths"])
-    out = {"workload": "GP interpreter, DS1 DAG (934 patterns, 612 PLVs, 181 GPCSPs)", "repeats": args.repeats}
+    out = {"workload": "GP interpreter, DS1 DAG (934 patterns, 612 PLVs, 181 GPCSPs)", "repeats": repeats}
     for name in ("populate_plvs", "compute_likelihoods", "marginal_likelihood", "branch_length_optimization",
                  "optimize_sbn_parameters"):
         program = fx["program_" + name]
         engine.process_operations(fx["program_populate_plvs"])  # a defined state; warm-up
         kernel, wall = [], []
-        for _ in range(args.repeats):
+        for _ in range(repeats):
             if name == "branch_length_optimization":
                 engine.set_branch_lengths(fx["initial_branch_lengths"])
                 engine.process_operations(fx["program_populate_plvs"])
@@ -48,7 +45,14 @@ def main():
         out[name] = {"words": int(program.size), "kernel_ms": float(np.median(kernel)),
                      "call_ms": float(np.median(wall))}
     out["log_marginal_likelihood"] = float(engine.get_log_marginal_likelihood())
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--repeats", type=int, default=20)
+    args = parser.parse_args()
+    print(json.dumps(measure(args.repeats)))
 
 
 if __name__ == "__main__":
