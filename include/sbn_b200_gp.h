@@ -100,18 +100,27 @@ int sbnb_gp_process_operations(sbnb_gp_engine* engine, const int32_t* program, i
 
 /*
  * The schedule the device runs for `program` (host only, no device needed; what
- * sbnb_gp_process_operations does first): the same records re-ordered by dependency level --
- * an op's level is one more than the highest level of the ops it must follow (read after
- * write, write after write, write after read over PLVs, rescaling counts, q, branch lengths,
- * log-likelihood rows, the log-marginal vector) -- and inside a level by kind, so that every
- * value is computed by the same arithmetic as in the reference's sequential order
- * (GPEngine::ProcessOperations, gp_engine.cpp:167-171).  Word 0 of the first record of a run of
- * mutually independent records of one kind carries the run length in bits 8 and up (the
- * interpreter issues their loads together); the opcode is word 0 & 0xff.  out receives
- * word_count words.
+ * sbnb_gp_process_operations does first):
+ *   - a run of adjacent IncrementWithWeightedEvolvedPLV records into one PLV (a node's
+ *     increments, gp_dag.cpp:264-290) becomes one record of internal kind 10 -- dest, n,
+ *     (gpcsp, src) x n, n <= 4 -- whose sources are loaded together and added in the
+ *     reference's order; when the PLV's last writer is a ZeroPLV nobody has read since, the
+ *     record (or the single increment) carries bit 30 of word 0 ("fresh": the sum starts from
+ *     0, dest is not loaded: 0 + x = x exactly) and that ZeroPLV carries bit 30 too (it only
+ *     clears the rescaling count);
+ *   - the records are re-ordered by dependency level -- an op's level is one more than the
+ *     highest level of the ops it must follow (read after write, write after write, write
+ *     after read over PLVs, rescaling counts, q, branch lengths, log-likelihood rows, the
+ *     log-marginal vector) -- and inside a level by kind, so that every value is computed
+ *     by the same arithmetic as in the reference's sequential order
+ *     (GPEngine::ProcessOperations, gp_engine.cpp:167-171);
+ *   - word 0 of the first record of a run of mutually independent records of one kind
+ *     carries the run length in bits 8..15 (the interpreter issues their loads together);
+ *     the opcode is word 0 & 0xff.
+ * out must hold word_count words; *out_word_count (<= word_count) of them are written.
  */
 int sbnb_gp_schedule_program(int32_t plv_count, int32_t gpcsp_count, const int32_t* program,
-                             int64_t word_count, int32_t* out);
+                             int64_t word_count, int32_t* out, int64_t* out_word_count);
 
 /* gp_engine.cpp:193-209. */
 int sbnb_gp_set_branch_lengths(sbnb_gp_engine* engine, const double* branch_lengths);

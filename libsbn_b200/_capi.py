@@ -116,7 +116,8 @@ SIGNATURES.update({
     "sbnb_gp_set_substitution_model": (_c.c_int, [_c.c_void_p, _c.c_char_p, _P(_c.c_double), _c.c_int32]),
     "sbnb_gp_set_site_model": (_c.c_int, [_c.c_void_p, _c.c_char_p, _P(_c.c_double), _c.c_int32]),
     "sbnb_gp_category_count": (_c.c_int32, [_c.c_void_p]),
-    "sbnb_gp_schedule_program": (_c.c_int, [_c.c_int32, _c.c_int32, _P(_c.c_int32), _c.c_int64, _P(_c.c_int32)]),
+    "sbnb_gp_schedule_program": (_c.c_int, [_c.c_int32, _c.c_int32, _P(_c.c_int32), _c.c_int64, _P(_c.c_int32),
+                                          _P(_c.c_int64)]),
     "sbnb_gp_set_branch_lengths": _GP_GET,
     "sbnb_gp_set_branch_lengths_to_constant": (_c.c_int, [_c.c_void_p, _c.c_double]),
     "sbnb_gp_get_branch_lengths": _GP_GET,

@@ -174,6 +174,9 @@ __device__ __forceinline__ double LogAdd(double x, double y) {
 // CTA has posted r + 1, i.e. after every CTA has read r.
 constexpr int kGpMaxGridBlocks = 160;
 constexpr int kGpMaxCategories = 8;
+constexpr int kGpChain = 4;                        // sources of one fused accumulation
+constexpr int kGpFlag = 1 << 30;                   // word 0: ZeroPLV clears the count only / an accumulation starts fresh
+constexpr int SBNB_GP_INTERNAL_EVOLVE_SUM = 10;    // dest, n, (gpcsp, src) x n: produced by CompileProgram only
 #ifndef SBNB_GP_BATCH_OPS
 #define SBNB_GP_BATCH_OPS 2
 #endif
@@ -287,6 +290,15 @@ struct Reducer {
     unsigned long long bits[1] = {static_cast<unsigned long long>(__double_as_longlong(v))};
     Exchange<1, false>(bits);
     return __longlong_as_double(static_cast<long long>(bits[0]));
+  }
+  template <int COUNT>
+  __device__ void Sums(double (&values)[COUNT]) {
+    unsigned long long bits[COUNT];
+#pragma unroll
+    for (int i = 0; i < COUNT; i++) bits[i] = static_cast<unsigned long long>(__double_as_longlong(values[i]));
+    Exchange<COUNT, false>(bits);
+#pragma unroll
+    for (int i = 0; i < COUNT; i++) values[i] = __longlong_as_double(static_cast<long long>(bits[i]));
   }
   // Every thread of the launch has got here.
   __device__ void Barrier() { Sum(0.0); }
@@ -448,13 +460,15 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
     // loads are issued together, and their reductions travel in one exchange.
     const int word0 = program[pc];
     const int opcode = word0 & 0xff;
-    const int batch = max(word0 >> 8, 1);
+    const int batch = max((word0 >> 8) & 0xff, 1);
     switch (opcode) {
       case SBNB_GP_ZERO_PLV: {  // gp_engine.cpp:48-51
         const double zero[4] = {0.0, 0.0, 0.0, 0.0};
         for (int u = 0; u < batch; u++) {
           const int dest = program[pc + 2 * u + 1];
-          for (int64_t k = first; k < E; k += step) StoreState(plv(dest), k, zero);
+          // (flagged: the next writer overwrites the whole PLV without reading it -- count only)
+          if (!(program[pc + 2 * u] & kGpFlag))
+            for (int64_t k = first; k < E; k += step) StoreState(plv(dest), k, zero);
           set_count(dest, 0);
         }
         pc += 2 * batch;
@@ -476,12 +490,14 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         const double* src_plv[kGpBatch];
         int gpcsp[kGpBatch];
         double factor[kGpBatch];
+        bool fresh[kGpBatch];  // the sum starts from 0: dest is not loaded
         int faulty = -1;  // (no return inside the unrolled loops: they must stay unrolled for the arrays to be registers)
 #pragma unroll
         for (int u = 0; u < kGpBatch; u++) {
           if (u < batch) {
             const int dest = program[pc + 4 * u + 1], src = program[pc + 4 * u + 3];
             gpcsp[u] = program[pc + 4 * u + 2];
+            fresh[u] = (program[pc + 4 * u] & kGpFlag) != 0;
             dest_plv[u] = plv(dest);
             src_plv[u] = plv(src);
             const int difference = counts[src] - counts[dest];
@@ -500,7 +516,11 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
           for (int u = 0; u < kGpBatch; u++) {
             if (u < batch) {
               LoadState(src_plv[u], k, s[u]);
-              LoadState(dest_plv[u], k, d[u]);
+              if (fresh[u]) {
+                d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.0;
+              } else {
+                LoadState(dest_plv[u], k, d[u]);
+              }
             }
           }
 #pragma unroll
@@ -520,6 +540,52 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
           }
         }
         pc += 4 * batch;
+        break;
+      }
+      case SBNB_GP_INTERNAL_EVOLVE_SUM: {  // a run of gp_engine.cpp:64-82 into one PLV (CompileProgram)
+        const int dest = program[pc + 1], sources = program[pc + 2];
+        const bool fresh = (word0 & kGpFlag) != 0;
+        double* const dest_plv = plv(dest);
+        const double* src_plv[kGpChain];
+        int gpcsp[kGpChain];
+        double factor[kGpChain];
+        int faulty = -1;
+#pragma unroll
+        for (int u = 0; u < kGpChain; u++) {
+          if (u < sources) {
+            gpcsp[u] = program[pc + 3 + 2 * u];
+            const int src = program[pc + 4 + 2 * u];
+            src_plv[u] = plv(src);
+            const int difference = counts[src] - counts[dest];
+            if (difference < 0 && faulty < 0) faulty = u;
+            factor[u] = q[gpcsp[u]];
+            if (difference > 0) factor[u] *= pow(p.threshold, static_cast<double>(difference));
+          }
+        }
+        if (faulty >= 0) {
+          fault(kGpFaultDestRescaling, pc);
+          return;
+        }
+        for (int64_t k = first; k < E; k += step) {
+          double s[kGpChain][4], d[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int u = 0; u < kGpChain; u++)
+            if (u < sources) LoadState(src_plv[u], k, s[u]);
+          if (!fresh) LoadState(dest_plv, k, d);
+#pragma unroll
+          for (int u = 0; u < kGpChain; u++) {  // (added in the reference's order)
+            if (u < sources) {
+              double m[16];
+              load_matrix(gpcsp[u], m);
+#pragma unroll
+              for (int i = 0; i < 4; i++)
+                d[i] += factor[u] * fma(m[i * 4 + 3], s[u][3], fma(m[i * 4 + 2], s[u][2], fma(m[i * 4 + 1], s[u][1], m[i * 4] * s[u][0])));
+              asm volatile("" ::: "memory");
+            }
+          }
+          StoreState(dest_plv, k, d);
+        }
+        pc += 3 + 2 * sources;
         break;
       }
       case SBNB_GP_MULTIPLY: {  // gp_engine.cpp:111-117 + RescalePLVIfNeeded 298-320
@@ -798,10 +864,28 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
           // the same bits)
           const bool keep = length <= plan.scratch;
           double log_norm = 0.0;
-          for (int g = start; g < stop; g++) {
-            const double value = (use_hybrid ? p.hybrid[g] : row_sum(g)) + log(q[g]);
-            if (keep) scratch[g - start] = value;
-            log_norm = (g == start) ? value : LogAdd(log_norm, value);
+          for (int g0 = start; g0 < stop; g0 += 4) {
+            // (four rows per exchange; every sum is reduced in the same order as one at a time)
+            double sums[4] = {0.0, 0.0, 0.0, 0.0};
+            if (!use_hybrid) {
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                if (g0 + u < stop) {
+                  const double* row = p.log_likelihoods + static_cast<size_t>(g0 + u) * P;
+                  for (int64_t k = first; k < P; k += stride) sums[u] = fma(row[k], p.weights[k], sums[u]);
+                }
+              }
+              reduce.Sums(sums);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int g = g0 + u;
+              if (g < stop) {
+                const double value = (use_hybrid ? p.hybrid[g] : sums[u]) + log(q[g]);
+                if (keep) scratch[g - start] = value;
+                log_norm = (g == start) ? value : LogAdd(log_norm, value);
+              }
+            }
           }
           if (keep) {
             // every thread must have read q[start..stop) before anyone overwrites it
@@ -1342,17 +1426,111 @@ void SetCategories(sbnb_gp_engine* e, int categories, const double* rates, const
 
 void CompileProgram(int32_t plv_count, int32_t gpcsp_count, const int32_t* program, int64_t word_count,
                     CompiledProgram* out) {
+  // ---- pass 1: the caller's records; runs of IncrementWithWeightedEvolvedPLV into one PLV
+  // (the reference emits a node's increments side by side, gp_dag.cpp:264-290) become ONE
+  // record -- SBNB_GP_INTERNAL_EVOLVE_SUM: dest, n, (gpcsp, src) x n, at most kGpChain sources --
+  // that loads every source at once and adds them in the reference's order; and when the PLV
+  // was last written by a ZeroPLV nobody has read since, the sum starts from 0 without
+  // loading it ("fresh") and that ZeroPLV only clears the rescaling count: 0 + x = x exactly.
   struct Op {
-    int32_t at, words, opcode, level;
+    int32_t at;                 // word offset in the caller's program (of its first record)
+    int32_t opcode, level = 0;
+    std::vector<int32_t> words;  // the record as the device sees it (word 0 without its batch length)
   };
-  // last writer's level, and the highest level among the readers since, per resource
+  static const bool fusing = EnvInt("SBNB_GP_FUSE", 1) != 0;
+  std::vector<Op> ops;
+  {
+    std::vector<int32_t> zeroed_by(plv_count, -1);  // index in `ops` of an unread ZeroPLV of the PLV, or -1
+    auto touch = [&](int32_t plv_index) { zeroed_by[plv_index] = -1; };
+    int64_t pc = 0;
+    while (pc < word_count) {
+      const int32_t* w = program + pc;
+      const int opcode = w[0];
+      Op op;
+      op.at = static_cast<int32_t>(pc);
+      op.opcode = opcode;
+      int32_t size = 0;
+      switch (opcode) {
+        case SBNB_GP_ZERO_PLV:
+          size = 2;
+          break;
+        case SBNB_GP_SET_TO_STATIONARY:
+          size = 3;
+          touch(w[1]);
+          break;
+        case SBNB_GP_INCREMENT_WITH_EVOLVED: {
+          size = 4;
+          if (!fusing) {
+            touch(w[1]), touch(w[3]);
+            break;
+          }
+          const int32_t dest = w[1];
+          std::vector<std::pair<int32_t, int32_t>> sources;  // (gpcsp, src)
+          int64_t next = pc;
+          while (next < word_count && program[next] == SBNB_GP_INCREMENT_WITH_EVOLVED && program[next + 1] == dest &&
+                 program[next + 3] != dest && static_cast<int>(sources.size()) < kGpChain) {
+            sources.emplace_back(program[next + 2], program[next + 3]);
+            next += 4;
+          }
+          if (sources.empty()) {  // (dest == src: left as it is)
+            touch(w[1]);
+            break;
+          }
+          const bool fresh = zeroed_by[dest] >= 0;
+          if (fresh) ops[zeroed_by[dest]].words[0] |= kGpFlag;  // that ZeroPLV: rescaling count only
+          touch(dest);
+          for (const auto& source : sources) touch(source.second);
+          if (sources.size() == 1) {
+            op.words = {SBNB_GP_INCREMENT_WITH_EVOLVED | (fresh ? kGpFlag : 0), dest, sources[0].first, sources[0].second};
+          } else {
+            op.opcode = SBNB_GP_INTERNAL_EVOLVE_SUM;
+            op.words = {SBNB_GP_INTERNAL_EVOLVE_SUM | (fresh ? kGpFlag : 0), dest, static_cast<int32_t>(sources.size())};
+            for (const auto& source : sources) op.words.insert(op.words.end(), {source.first, source.second});
+          }
+          size = static_cast<int32_t>(next - pc);
+          break;
+        }
+        case SBNB_GP_MULTIPLY:
+          size = 4;
+          touch(w[1]), touch(w[2]), touch(w[3]);
+          break;
+        case SBNB_GP_LIKELIHOOD:
+        case SBNB_GP_INCREMENT_MARGINAL:
+          size = 4;
+          touch(opcode == SBNB_GP_LIKELIHOOD ? w[2] : w[1]), touch(w[3]);
+          break;
+        case SBNB_GP_OPTIMIZE_BRANCH_LENGTH:
+          size = 4;
+          touch(w[1]), touch(w[2]);
+          break;
+        case SBNB_GP_UPDATE_SBN_PROBABILITIES:
+          size = 3;
+          break;
+        case SBNB_GP_RESET_MARGINAL_LIKELIHOOD:
+          size = 1;
+          break;
+        case SBNB_GP_PREP_FOR_MARGINALIZATION:
+          size = 3 + w[2];
+          break;
+        default:
+          Fail(SBNB_ERR_INVALID_ARGUMENT, "Unknown GP opcode " + std::to_string(opcode) + ".");
+      }
+      if (op.words.empty()) op.words.assign(w, w + size);
+      ops.push_back(std::move(op));
+      if (opcode == SBNB_GP_ZERO_PLV && fusing) zeroed_by[w[1]] = static_cast<int32_t>(ops.size()) - 1;
+      if (opcode == SBNB_GP_ZERO_PLV && !fusing) touch(w[1]);
+      pc += size;
+    }
+  }
+
+  // ---- pass 2: dependency levels.  Last writer's level, and the highest level among the
+  // readers since, per resource.
   struct Track {
     int32_t written = -1, read = -1;
   };
   const size_t gpcsps = std::max(gpcsp_count, 1);
   std::vector<Track> plv(plv_count), count(plv_count), prior(gpcsps), length(gpcsps), row(gpcsps);
   Track marginal;
-  std::vector<Op> ops;
   int32_t level = 0;
   auto reads = [&](Track& t) { level = std::max(level, t.written + 1); };
   auto writes = [&](Track& t) { level = std::max(level, std::max(t.written, t.read) + 1); };
@@ -1361,76 +1539,70 @@ void CompileProgram(int32_t plv_count, int32_t gpcsp_count, const int32_t* progr
     t.written = level;
     t.read = -1;
   };
-  int64_t pc = 0;
-  while (pc < word_count) {
-    const int32_t* w = program + pc;
-    const int opcode = w[0];
-    int32_t size = 0;
+  for (Op& op : ops) {
+    const int32_t* w = op.words.data();
+    const bool flagged = (w[0] & kGpFlag) != 0;
     level = 0;
     // two passes over the op's resources: find its level, then record it
     for (int pass = 0; pass < 2; pass++) {
       auto R = [&](Track& t) { pass == 0 ? reads(t) : did_read(t); };
       auto W = [&](Track& t) { pass == 0 ? writes(t) : did_write(t); };
-      switch (opcode) {
+      switch (op.opcode) {
         case SBNB_GP_ZERO_PLV:
-          size = 2;
-          W(plv[w[1]]), W(count[w[1]]);
+          if (!flagged) W(plv[w[1]]);
+          W(count[w[1]]);
           break;
         case SBNB_GP_SET_TO_STATIONARY:
-          size = 3;
           R(prior[w[2]]), W(plv[w[1]]), W(count[w[1]]);
           break;
         case SBNB_GP_INCREMENT_WITH_EVOLVED:
-          size = 4;
-          R(plv[w[3]]), R(count[w[3]]), R(count[w[1]]), R(prior[w[2]]), R(length[w[2]]), R(plv[w[1]]), W(plv[w[1]]);
+          R(plv[w[3]]), R(count[w[3]]), R(count[w[1]]), R(prior[w[2]]), R(length[w[2]]);
+          if (!flagged) R(plv[w[1]]);
+          W(plv[w[1]]);
+          break;
+        case SBNB_GP_INTERNAL_EVOLVE_SUM:
+          for (int i = 0; i < w[2]; i++) R(plv[w[4 + 2 * i]]), R(count[w[4 + 2 * i]]), R(prior[w[3 + 2 * i]]), R(length[w[3 + 2 * i]]);
+          R(count[w[1]]);
+          if (!flagged) R(plv[w[1]]);
+          W(plv[w[1]]);
           break;
         case SBNB_GP_MULTIPLY:
-          size = 4;
           R(plv[w[2]]), R(plv[w[3]]), R(count[w[2]]), R(count[w[3]]), W(plv[w[1]]), W(count[w[1]]);
           break;
         case SBNB_GP_LIKELIHOOD:
-          size = 4;
           R(plv[w[2]]), R(plv[w[3]]), R(count[w[2]]), R(count[w[3]]), R(length[w[1]]), W(row[w[1]]);
           break;
         case SBNB_GP_OPTIMIZE_BRANCH_LENGTH:
-          size = 4;
           R(plv[w[1]]), R(plv[w[2]]), R(count[w[1]]), R(count[w[2]]), R(length[w[3]]), W(length[w[3]]);
           break;
         case SBNB_GP_UPDATE_SBN_PROBABILITIES:
-          size = 3;
           for (int g = w[1]; g < w[2]; g++) R(row[g]), R(prior[g]);
           for (int g = w[1]; g < w[2]; g++) W(prior[g]);
           break;
         case SBNB_GP_RESET_MARGINAL_LIKELIHOOD:
-          size = 1;
           W(marginal);
           break;
         case SBNB_GP_INCREMENT_MARGINAL:
-          size = 4;
           R(plv[w[1]]), R(plv[w[3]]), R(count[w[1]]), R(count[w[3]]), R(prior[w[2]]), R(marginal), W(marginal),
               W(row[w[2]]);
           break;
         case SBNB_GP_PREP_FOR_MARGINALIZATION:
-          size = 3 + w[2];
           for (int i = 0; i < w[2]; i++) R(count[w[3 + i]]);
           W(count[w[1]]);
           break;
-        default:
-          Fail(SBNB_ERR_INVALID_ARGUMENT, "Unknown GP opcode " + std::to_string(opcode) + ".");
       }
     }
-    ops.push_back({static_cast<int32_t>(pc), size, opcode, level});
-    pc += size;
+    op.level = level;
   }
   // by level, then kind (the scalar-only PrepForMarginalization first), then the reference's order
   static const bool reorder = EnvInt("SBNB_GP_LEVELS", 1) != 0;
   if (reorder)
-  std::stable_sort(ops.begin(), ops.end(), [](const Op& a, const Op& b) {
-    if (a.level != b.level) return a.level < b.level;
-    const int ka = a.opcode == SBNB_GP_PREP_FOR_MARGINALIZATION ? -1 : a.opcode;
-    const int kb = b.opcode == SBNB_GP_PREP_FOR_MARGINALIZATION ? -1 : b.opcode;
-    return ka < kb;
-  });
+    std::stable_sort(ops.begin(), ops.end(), [](const Op& a, const Op& b) {
+      if (a.level != b.level) return a.level < b.level;
+      const int ka = a.opcode == SBNB_GP_PREP_FOR_MARGINALIZATION ? -1 : a.opcode;
+      const int kb = b.opcode == SBNB_GP_PREP_FOR_MARGINALIZATION ? -1 : b.opcode;
+      return ka < kb;
+    });
   auto batch_limit = [](int opcode) {
     switch (opcode) {
       case SBNB_GP_ZERO_PLV:
@@ -1459,8 +1631,8 @@ void CompileProgram(int32_t plv_count, int32_t gpcsp_count, const int32_t* progr
     for (size_t r = 0; r < run; r++) {
       const Op& op = ops[i + r];
       out->origin.emplace_back(static_cast<int32_t>(out->words.size()), op.at);
-      out->words.insert(out->words.end(), program + op.at, program + op.at + op.words);
-      if (r == 0) out->words[out->words.size() - op.words] |= static_cast<int32_t>(run) << 8;
+      out->words.insert(out->words.end(), op.words.begin(), op.words.end());
+      if (r == 0) out->words[out->words.size() - op.words.size()] |= static_cast<int32_t>(run) << 8;
     }
     i += run;
   }
@@ -1588,12 +1760,12 @@ int sbnb_gp_process_operations(sbnb_gp_engine* e, const int32_t* program, int64_
                                 static_cast<size_t>(2) * e->blocks * 2 * kGpReduceValues * sizeof(double), e->stream));
     GpParams p = e->params;
     p.program = compiled->device.get();
-    p.word_count = word_count;
+    p.word_count = static_cast<int64_t>(compiled->words.size());
     SBNB_CUDA(cudaEventRecord(e->begin, e->stream));
     GpSmemPlan plan = e->plan;
-    if (plan.bytes + static_cast<size_t>(word_count) * sizeof(int32_t) <= kGpSmemBudget) {
-      plan.program_words = static_cast<int32_t>(word_count);
-      plan.bytes += static_cast<size_t>(word_count) * sizeof(int32_t);
+    if (plan.bytes + compiled->words.size() * sizeof(int32_t) <= kGpSmemBudget) {
+      plan.program_words = static_cast<int32_t>(compiled->words.size());
+      plan.bytes += compiled->words.size() * sizeof(int32_t);
     }
     // (multi-block launches were sized for the whole budget)
     const size_t smem_bytes = e->blocks == 1 ? plan.bytes : kGpSmemBudget;
@@ -1664,7 +1836,7 @@ int sbnb_gp_set_site_model(sbnb_gp_engine* e, const char* site, const double* pa
 int32_t sbnb_gp_category_count(const sbnb_gp_engine* e) { return e ? e->params.categories : 0; }
 
 int sbnb_gp_schedule_program(int32_t plv_count, int32_t gpcsp_count, const int32_t* program, int64_t word_count,
-                             int32_t* out) {
+                             int32_t* out, int64_t* out_word_count) {
   return Guard([&] {
     Require(plv_count >= 0 && gpcsp_count >= 0, "Negative PLV / GPCSP count.");
     Require(word_count >= 0 && (program != nullptr || word_count == 0), "NULL program.");
@@ -1672,7 +1844,9 @@ int sbnb_gp_schedule_program(int32_t plv_count, int32_t gpcsp_count, const int32
     ValidateProgram(GpShape{plv_count, gpcsp_count}, program, word_count);
     CompiledProgram compiled;
     CompileProgram(plv_count, gpcsp_count, program, word_count, &compiled);
+    Require(static_cast<int64_t>(compiled.words.size()) <= word_count, "The schedule outgrew the program.");
     std::copy(compiled.words.begin(), compiled.words.end(), out);
+    if (out_word_count) *out_word_count = static_cast<int64_t>(compiled.words.size());
   });
 }
 

@@ -67,13 +67,16 @@ class GPOperations:
 
 
 def schedule_program(plv_count, gpcsp_count, program):
-    """The schedule the device runs for `program` (sbnb_gp_schedule_program; host only): the records
-    re-ordered by dependency level, the first record of a batch tagged with its length in bits 8+."""
+    """The schedule the device runs for `program` (sbnb_gp_schedule_program; host only): runs of
+    increments into one PLV fused (internal kind 10; bit 30 of word 0 = "fresh" / count-only ZeroPLV), the
+    records re-ordered by dependency level, the first record of a batch tagged with its length in bits 8..15."""
+    import ctypes
     program = np.ascontiguousarray(program, dtype=np.int32)
     out = np.empty_like(program)
+    count = ctypes.c_int64(0)
     _capi.check(_capi.load().sbnb_gp_schedule_program(int(plv_count), int(gpcsp_count), _capi.as_int32_ptr(program),
-                                                      program.size, _capi.as_int32_ptr(out)))
-    return out
+                                                      program.size, _capi.as_int32_ptr(out), ctypes.byref(count)))
+    return out[:count.value].copy()
 
 
 def _tips(tips):

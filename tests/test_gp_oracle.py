@@ -87,16 +87,31 @@ def test_asserts_surface():
 
 
 # ---- the device's schedule of a program (sbnb_gp_schedule_program; host code of libsbn_b200.so)
+FLAG = 1 << 30
+
+
 def _records(program):
-    """(kind, fields) per record; the batch length of word 0 (bits 8+) is dropped."""
+    """(kind, fields, batch length, flag) per record of a (scheduled) program."""
     size = {0: 2, 1: 3, 2: 4, 3: 4, 4: 4, 5: 4, 6: 3, 7: 1, 8: 4}
     program = [int(w) for w in program]
     pc, out = 0, []
     while pc < len(program):
         kind = program[pc] & 0xff
-        words = size[kind] if kind != 9 else 3 + program[pc + 2]
-        out.append((kind, tuple(program[pc + 1:pc + words]), program[pc] >> 8))
+        words = size[kind] if kind in size else (3 + program[pc + 2] if kind == 9 else 3 + 2 * program[pc + 2])
+        out.append((kind, tuple(program[pc + 1:pc + words]), (program[pc] >> 8) & 0xff, bool(program[pc] & FLAG)))
         pc += words
+    return out
+
+
+def _unfused(records):
+    """The reference's records behind a schedule: fused accumulations split into their increments."""
+    out = []
+    for kind, fields, _, _ in records:
+        if kind == 10:
+            dest, count = fields[:2]
+            out += [(2, (dest, fields[2 + 2 * i], fields[3 + 2 * i])) for i in range(count)]
+        else:
+            out.append((kind, fields))
     return out
 
 
@@ -110,23 +125,28 @@ def test_schedule_is_a_batched_permutation_of_the_program(name, programs):
     fx = load_fixture("gp_" + name)
     for key in programs:
         scheduled = schedule_program(fx["plv_count"], fx["gpcsp_count"], fx[key])
+        assert scheduled.size <= fx[key].size
         before, after = _records(fx[key]), _records(scheduled)
-        assert sorted((k, f) for k, f, _ in before) == sorted((k, f) for k, f, _ in after)
+        assert sorted(_unfused(before)) == sorted(_unfused(after))
         # batch lengths: a tagged record is followed by length - 1 untagged records of its kind
         i = 0
         while i < len(after):
-            kind, _, length = after[i]
+            kind, _, length, _ = after[i]
             assert length >= 1
             assert all(after[i + j][0] == kind and after[i + j][2] == 0 for j in range(1, length))
             i += length
     populate = _records(schedule_program(fx["plv_count"], fx["gpcsp_count"], fx["program_populate_plvs"]))
-    assert sum(1 for _, _, length in populate if length >= 1) < len(populate) / 2  # most ops ride in batches
+    assert sum(1 for record in populate if record[2] >= 1) < len(populate) / 2  # most ops ride in batches
+    assert any(kind == 10 and flag for kind, _, _, flag in populate)  # accumulations fused, starting fresh
+    assert any(kind == 0 and flag for kind, _, _, flag in populate)   # ... their ZeroPLVs reduced to the count
 
 
 @pytest.mark.parametrize("name", ["five_taxon", "hello_two_trees", "seven_taxon_all_trees", "five_taxon_threshold_0.5"])
 def test_scheduled_programs_compute_the_same_bits(name):
-    """Ops of one dependency level are independent: the re-ordered program run op by op on the
-    numpy oracle gives bit-identical PLVs, branch lengths, q and likelihoods."""
+    """Ops of one dependency level are independent, a fused accumulation adds in the reference's order,
+    and a PLV whose ZeroPLV was reduced to its count is overwritten before anybody reads it (the oracle
+    poisons it): the scheduled program run record by record on the numpy oracle gives bit-identical
+    PLVs, branch lengths, q and likelihoods."""
     from libsbn_b200.gp_engine import schedule_program
     fx = load_fixture("gp_" + name)
     engines = [gp_cases.make_engine(factory, fx), gp_cases.make_engine(factory, fx)]
@@ -136,26 +156,13 @@ def test_scheduled_programs_compute_the_same_bits(name):
         if key not in fx:
             continue
         engines[0].process_operations(fx[key])
-        scheduled = schedule_program(fx["plv_count"], fx["gpcsp_count"], fx[key])
-        engines[1].process_operations(np.array([w & 0xff if i in _starts(scheduled) else w
-                                                for i, w in enumerate(scheduled)], dtype=np.int32))
+        engines[1].process_operations(schedule_program(fx["plv_count"], fx["gpcsp_count"], fx[key]))
         assert np.array_equal(engines[0].plvs, engines[1].plvs)
         assert np.array_equal(engines[0].branch_lengths, engines[1].branch_lengths)
         assert np.array_equal(engines[0].q, engines[1].q)
         assert np.array_equal(engines[0].rescaling_counts, engines[1].rescaling_counts)
         assert np.array_equal(engines[0].log_likelihoods, engines[1].log_likelihoods, equal_nan=True)
         assert np.array_equal(engines[0].log_marginal_likelihood, engines[1].log_marginal_likelihood)
-
-
-def _starts(program):
-    """Word offsets of the records' first words."""
-    size = {0: 2, 1: 3, 2: 4, 3: 4, 4: 4, 5: 4, 6: 3, 7: 1, 8: 4}
-    pc, out = 0, set()
-    while pc < len(program):
-        out.add(pc)
-        kind = int(program[pc]) & 0xff
-        pc += size[kind] if kind != 9 else 3 + int(program[pc + 2])
-    return out
 
 
 # ---- GP beyond JC69 (SURVEY.md 8f-4; not in the reference): pinned through a single-tree DAG

@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-(timeout 1500 python -m pytest tests -m gpu -x -q) > gpurun_out/s35_pytest.log 2>&1; tail -4 gpurun_out/s35_pytest.log
-(time timeout 1200 python bench.py) > gpurun_out/s35_bench.json 2> gpurun_out/s35_bench.err; tail -c 3000 gpurun_out/s35_bench.json; tail -5 gpurun_out/s35_bench.err
+(timeout 900 python -m pytest tests/test_gp_gpu.py tests/test_integration_gpu.py -x -q) > gpurun_out/s37_pytest.log 2>&1; tail -5 gpurun_out/s37_pytest.log
+timeout 120 python tools/gp_kernel_time.py 2>&1 | tail -1
+SBNB_GP_FUSE=0 timeout 120 python tools/gp_kernel_time.py 2>&1 | tail -1
+timeout 600 python tools/gp_bench.py 2>&1 | tail -3
