@@ -856,7 +856,8 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
           auto row_sum = [&](int g) -> double {
             const double* row = p.log_likelihoods + static_cast<size_t>(g) * P;
             double local = 0.0;
-            for (int64_t k = first; k < P; k += stride) local = fma(row[k], p.weights[k], local);
+            for (int64_t e = first; e < E; e += stride)
+              if (my_category == 0) local = fma(row[e >> p.log2_categories], p.weights[e >> p.log2_categories], local);
             return reduce.Sum(local);
           };
           // log of the unnormalised posterior per GPCSP, folded with LogAdd in index order;
@@ -872,7 +873,9 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
               for (int u = 0; u < 4; u++) {
                 if (g0 + u < stop) {
                   const double* row = p.log_likelihoods + static_cast<size_t>(g0 + u) * P;
-                  for (int64_t k = first; k < P; k += stride) sums[u] = fma(row[k], p.weights[k], sums[u]);
+                  // (a pattern's values are read by the thread that wrote them: its category-0 lane)
+                  for (int64_t e = first; e < E; e += stride)
+                    if (my_category == 0) sums[u] = fma(row[e >> p.log2_categories], p.weights[e >> p.log2_categories], sums[u]);
                 }
               }
               reduce.Sums(sums);
@@ -904,7 +907,9 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         break;
       }
       case SBNB_GP_RESET_MARGINAL_LIKELIHOOD: {  // gp_engine.cpp:84-86
-        for (int64_t k = first; k < P; k += stride) p.log_marginal[k] = -INFINITY;
+        // (by the thread that accumulates the pattern in IncrementMarginalLikelihood: its category-0 lane)
+        for (int64_t e = first; e < E; e += stride)
+          if (my_category == 0) p.log_marginal[e >> p.log2_categories] = -INFINITY;
         pc += 1;
         break;
       }
