@@ -15,8 +15,8 @@
 //     flow runs redundantly in every thread on identical, deterministically
 //     reduced objective values, so no host round trip happens inside the search;
 //   * UpdateSBNProbabilities' per-GPCSP weighted sums (gp_engine.cpp:136-153).
-// Scalars (rescaling counts, branch lengths, q, the transition matrices of all
-// GPCSPs) live in shared memory and are written redundantly with identical values.
+// Scalars (rescaling counts per warp, q, the transition matrices of all GPCSPs) live in
+// shared memory; every CTA keeps its own copies and computes the same values.
 //
 // At DS1 size an op is a chain of latencies, not arithmetic or bandwidth (measured: 0.13
 // instructions per cycle per warp, fixed-latency and scoreboard stalls), so the work is
@@ -372,9 +372,9 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
     for (int g = threadIdx.x; g < G; g += blockDim.x) q_smem[g] = p.q[g];
   // Warps drift apart between reductions, so a shared copy of the rescaling
   // counts could show a lagging warp a value from its future; every warp keeps
-  // (and redundantly updates) its own copy.  Branch lengths, matrices and q are only
-  // written right after a barrier of the same op, which orders them after every
-  // older read, and every warp writes the same bits.
+  // (updated by its lane 0) its own copy.  Matrices and q are only written right after a
+  // barrier of the same op, which orders the write after every older read -- by one warp /
+  // one thread per entry -- and a CTA barrier publishes them (racecheck-clean).
   int32_t* const counts =
       plan.counts ? counts_smem + static_cast<size_t>(warp) * p.plv_count
                   : p.counts + (static_cast<size_t>(blockIdx.x) * (kGpMaxBlockThreads / 32) + warp) * p.plv_count;
@@ -382,9 +382,13 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
     for (int i = lane; i < p.plv_count; i += 32) counts[i] = p.counts[i];
   // (the first copy in global memory is what the getters and the other kernels read)
   const bool mirrors_counts = plan.counts && blockIdx.x == 0 && warp == 0;
-  auto set_count = [&](int index, int value) {
-    counts[index] = value;
-    if (mirrors_counts) p.counts[index] = value;
+  auto set_count = [&](int index, int value) {  // (warp-uniform call sites: one lane writes the warp's copy)
+    __syncwarp();  // (the other lanes' reads of older ops)
+    if (lane == 0) {
+      counts[index] = value;
+      if (mirrors_counts) p.counts[index] = value;
+    }
+    __syncwarp();
   };
   __syncthreads();
 
@@ -832,21 +836,22 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
         // (every warp has passed the last evaluation's barrier: nobody still reads the old values)
         const double new_length = (fx > current_value) ? exp(current_log_branch_length) : exp(x);
         p.branch_lengths[gpcsp] = new_length;
-        WarpCategoryMatrices(p, new_length, matrices + static_cast<size_t>(gpcsp) * C * 16);
-        __syncwarp();
+        if (warp == 0) WarpCategoryMatrices(p, new_length, matrices + static_cast<size_t>(gpcsp) * C * 16);
+        __syncthreads();
         pc += 4;
         break;
       }
       case SBNB_GP_UPDATE_SBN_PROBABILITIES: {  // gp_engine.cpp:136-153
         const int start = program[pc + 1], stop = program[pc + 2];
         const int length = stop - start;
-        auto set_q = [&](int g, double value) {
+        auto set_q = [&](int g, double value) {  // (by one thread of the CTA; the caller synchronises)
           q[g] = value;
-          if (plan.matrices) p.q[g] = value;  // (the copy the getters read)
+          if (plan.matrices && blockIdx.x == 0) p.q[g] = value;  // (the copy the getters read)
         };
         if (length == 1) {
           reduce.Barrier();  // lagging warps may still be reading q in an older op
-          set_q(start, 1.0);
+          if (threadIdx.x == 0) set_q(start, 1.0);
+          __syncthreads();
         } else if (length > 1) {
           // (a lagging warp may still be reading the scratch values of an older op)
           __syncthreads();
@@ -885,7 +890,7 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
               const int g = g0 + u;
               if (g < stop) {
                 const double value = (use_hybrid ? p.hybrid[g] : sums[u]) + log(q[g]);
-                if (keep) scratch[g - start] = value;
+                if (keep && threadIdx.x == 0) scratch[g - start] = value;
                 log_norm = (g == start) ? value : LogAdd(log_norm, value);
               }
             }
@@ -893,13 +898,16 @@ __global__ void __launch_bounds__(kGpMaxBlockThreads, 1) GpInterpretKernel(const
           if (keep) {
             // every thread must have read q[start..stop) before anyone overwrites it
             reduce.Barrier();
-            for (int g = start; g < stop; g++) set_q(g, exp(scratch[g - start] - log_norm));
+            for (int g = start + static_cast<int>(threadIdx.x); g < stop; g += blockDim.x)
+              set_q(g, exp(scratch[g - start] - log_norm));
+            __syncthreads();
           } else {
             // too long for the scratch: the second pass recomputes the same values (identical bits)
             for (int g = start; g < stop; g++) {
               const double updated = exp((use_hybrid ? p.hybrid[g] : row_sum(g)) + log(q[g]) - log_norm);
               reduce.Barrier();
-              set_q(g, updated);
+              if (threadIdx.x == 0) set_q(g, updated);
+              __syncthreads();
             }
           }
         }
