@@ -46,9 +46,19 @@ namespace {
 constexpr int kStates = 4;
 constexpr int kBlock = 128;
 
-struct DeviceOp {
+struct alignas(16) DeviceOp {
   int32_t dest, scale_write, child1, matrix1, child2, matrix2;
+  int32_t flags;  // what the host knows about the children (the pipelined kernel's cases)
+  int32_t pad;
+  // the same, as element offsets (the pipelined kernel adds its thread's offset: no 64-bit
+  // multiplications per op): partials in doubles -- a compact child in bytes of the state
+  // array --, the scale buffer in doubles (unused when scale_write < 0)
+  int64_t dest_at, child1_at, child2_at, scale_at;
 };
+static_assert(sizeof(DeviceOp) == 64, "op records are four 16-byte words");
+// child x is a compact tip / is the destination of the PREVIOUS op of the list (still in the
+// thread's registers: no load)
+enum : int32_t { kChild1Compact = 1, kChild2Compact = 2, kChild1Forward = 4, kChild2Forward = 8 };
 
 struct InstanceView {
   int32_t tips, buffers, P, C, matrices, scalers;
@@ -62,13 +72,19 @@ struct InstanceView {
   const double* pattern_weights;  // [P]
 };
 
+// The four states of one (pattern, category) in global memory: ONE 256-bit access (sm_100;
+// LDG.E.256 / STG.E.256), so a warp's request covers whole 128-byte lines -- two 128-bit halves
+// 32 bytes apart take twice the L1 wavefronts.  32-byte aligned: every partial and matrix row is.
 __device__ __forceinline__ void Load4(const double* src, double (&x)[4]) {
-  const double2 a = reinterpret_cast<const double2*>(src)[0], b = reinterpret_cast<const double2*>(src)[1];
-  x[0] = a.x, x[1] = a.y, x[2] = b.x, x[3] = b.y;
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(src));
 }
 __device__ __forceinline__ void Store4(double* dst, const double (&x)[4]) {
-  reinterpret_cast<double2*>(dst)[0] = make_double2(x[0], x[1]);
-  reinterpret_cast<double2*>(dst)[1] = make_double2(x[2], x[3]);
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+}
+// ... and in shared memory (16-byte aligned rows)
+__device__ __forceinline__ void LoadShared4(const double* src, double (&x)[4]) {
+  const double2 a = reinterpret_cast<const double2*>(src)[0], b = reinterpret_cast<const double2*>(src)[1];
+  x[0] = a.x, x[1] = a.y, x[2] = b.x, x[3] = b.y;
 }
 __device__ __forceinline__ double* Partial(const InstanceView& v, int buffer, int c, int64_t k) {
   return v.partials + ((static_cast<size_t>(buffer) * v.C + c) * v.P + k) * kStates;
@@ -126,40 +142,256 @@ __device__ __forceinline__ double OpTerm(const InstanceView& v, const DeviceOp& 
   return fmax(fmax(d[0], d[1]), fmax(d[2], d[3]));
 }
 
-// CT = 1, 2, 4, 8 or 16 rate categories: a thread owns one (pattern, category) -- category-major
-// inside the warp, so the 32 / CT lanes of a category read consecutive patterns (32 bytes
-// each: coalesced) -- for the whole op list of the call; the per-pattern maximum of a
-// rescaled op is taken over the pattern's CT lanes by shuffles.
-template <bool PRE, int CT>
-__global__ void __launch_bounds__(kBlock) UpdatePartialsLanesKernel(const InstanceView v,
-                                                                   const DeviceOp* __restrict__ ops, int op_count,
-                                                                   int cumulative) {
-  constexpr int kPerWarp = 32 / CT;  // patterns of a warp
-  const int lane = threadIdx.x & 31;
+// CT = 1, 2, 4, 8 or 16 rate categories: a thread owns K adjacent patterns of one category --
+// category-major inside the warp, so the 32 / CT lanes of a category read consecutive patterns
+// (32 K bytes each: coalesced) -- for the whole op list of the call.  The walk is a chain of
+// dependent global-memory round trips per thread (ncu of the first version: 66 % of the
+// stalls on the long scoreboard at half of the HBM peak), so:
+//   * a child that is the destination of the previous op is taken from registers (the host
+//     flags it: in a post-order list that is one child of nearly every op);
+//   * the other internal children of op o + 1 are requested right after the mat-vecs of op o
+//     have consumed op o's operands -- the rest of op o (maximum, division, logarithm, stores)
+//     and the other warps cover the latency;
+//   * op records and the two matrices of each op are staged in shared memory a chunk of ops at
+//     a time (a compact child's matrix transposed: column s is one 32-byte row), category
+//     blocks 144 bytes apart (no bank conflicts between the categories of a warp);
+//   * the cumulative scale buffer is read once, summed in a register in the op order and
+//     written once (the host checks that no op of the list writes the same buffer);
+//   * the per-pattern maximum of a rescaled op is taken over the pattern's CT lanes by
+//     shuffles, and the logarithms of CT rescaled ops are taken at once, one per category lane
+//     (a quarter of the instructions of the first version were the logarithm that one lane in
+//     CT needed);
+//   * a record carries its buffers as element offsets, and the four states of a (pattern,
+//     category) move as one 256-bit access.
+constexpr int kMatrixStride = 18;  // doubles between the category blocks of a staged matrix
+__host__ __device__ constexpr int ChunkOps(int CT) { return CT <= 4 ? 16 : (CT == 8 ? 8 : 4); }
+
+template <bool PRE, int CT, int K>
+__global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipelinedKernel(const InstanceView v,
+                                                                       const DeviceOp* __restrict__ ops, int op_count,
+                                                                       int cumulative, int cumulative_in_register) {
+  constexpr int kPerWarp = 32 / CT;  // pattern groups of a warp
+  constexpr int kChunk = ChunkOps(CT);
+  constexpr int kBlockPatterns = (kBlock / 32) * kPerWarp * K;
+  constexpr int kOpMatrixDoubles = 2 * CT * kMatrixStride;
+  constexpr int kOpEntries = 2 * CT * 16;  // matrix entries staged per op
+  constexpr unsigned kFull = 0xffffffffu;
+  __shared__ __align__(16) DeviceOp s_ops[kChunk];
+  __shared__ __align__(16) double s_matrix[kChunk * kOpMatrixDoubles];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane / kPerWarp;
-  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t first = warp * kPerWarp; first < v.P; first += warps * kPerWarp) {
-    const int64_t mine = first + lane % kPerWarp;
-    const bool active = mine < v.P;
-    const int64_t k = active ? mine : v.P - 1;  // (idle lanes shadow the last pattern and store nothing)
-    for (int o = 0; o < op_count; o++) {
-      const DeviceOp op = ops[o];
-      double d[4];
-      double largest = OpTerm<PRE>(v, op, c, k, d);
-      if (op.scale_write >= 0) {
+  // (the trip count is the same for every thread of a block: the chunk loop has barriers)
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * kBlockPatterns; base < v.P;
+       base += static_cast<int64_t>(gridDim.x) * kBlockPatterns) {
+    const int64_t first = base + static_cast<int64_t>(warp * kPerWarp + lane % kPerWarp) * K;
+    bool active[K];
+    const double* partial_at[K];  // this thread's (pattern, category) in partial buffer 0
+    const uint8_t* state_at[K];   // its pattern in compact buffer 0
+    double* scale_at[K];          // its pattern in scale buffer 0
 #pragma unroll
-        for (int s = kPerWarp; s < 32; s <<= 1) largest = fmax(largest, __shfl_xor_sync(0xffffffffu, largest, s));
-        if (largest == 0.0) largest = 1.0;
-        const double inverse = 1.0 / largest;
+    for (int j = 0; j < K; j++) {
+      active[j] = first + j < v.P;
+      const int64_t k = active[j] ? first + j : v.P - 1;  // (idle slots shadow the last pattern and store nothing)
+      partial_at[j] = v.partials + (static_cast<int64_t>(c) * v.P + k) * kStates;
+      state_at[j] = v.compact + k;
+      scale_at[j] = v.scale + k;
+    }
+    // The logarithms of the cumulative scale buffer are taken CT at a time: the pattern's
+    // lanes all hold the op's maximum, the lane of category (rescaled ops so far) % CT keeps
+    // it, and after CT rescaled ops every lane takes ONE logarithm; the terms are then added
+    // in op order (shuffles), each lane of the pattern keeping the same sum.
+    double cum[K], held[K];
+    int pending = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) d[i] *= inverse;
-        if (active && c == 0) {
-          v.scale[static_cast<size_t>(op.scale_write) * v.P + k] = largest;
-          if (cumulative >= 0) v.scale[static_cast<size_t>(cumulative) * v.P + k] += log(largest);
+    for (int j = 0; j < K; j++) {
+      held[j] = 1.0;
+      cum[j] = (cumulative >= 0 && cumulative_in_register) ? scale_at[j][static_cast<int64_t>(cumulative) * v.P] : 0.0;
+    }
+    auto flush_logarithms = [&]() {
+      double term[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) term[j] = log(held[j]);
+#pragma unroll
+      for (int i = 0; i < CT; i++) {
+        if (i < pending) {
+#pragma unroll
+          for (int j = 0; j < K; j++) cum[j] += __shfl_sync(kFull, term[j], lane % kPerWarp + i * kPerWarp);
         }
       }
-      if (active) Store4(Partial(v, op.dest, c, k), d);
+      pending = 0;
+    };
+    double d[K][4];    // the result of the previous op
+    double n1[K][4], n2[K][4];  // requested partials of the next op's children
+    int s1[K], s2[K];  // ... or their compact states
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      s1[j] = s2[j] = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) d[j][i] = n1[j][i] = n2[j][i] = 0.0;
+    }
+    auto request = [&](const DeviceOp& op) {
+      const int flags = op.flags;
+      if (flags & kChild1Compact) {
+#pragma unroll
+        for (int j = 0; j < K; j++) s1[j] = state_at[j][op.child1_at];
+      } else if (!(flags & kChild1Forward)) {
+#pragma unroll
+        for (int j = 0; j < K; j++) Load4(partial_at[j] + op.child1_at, n1[j]);
+      }
+      if (flags & kChild2Compact) {
+#pragma unroll
+        for (int j = 0; j < K; j++) s2[j] = state_at[j][op.child2_at];
+      } else if (!(flags & kChild2Forward)) {
+#pragma unroll
+        for (int j = 0; j < K; j++) Load4(partial_at[j] + op.child2_at, n2[j]);
+      }
+    };
+    // out[j] = M x[j] (a full partial; M row-major in shared memory)
+    auto evolve = [&](const double* m, const double (&x)[K][4], double (&out)[K][4]) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        double row[4];
+        LoadShared4(m + 4 * i, row);
+#pragma unroll
+        for (int j = 0; j < K; j++)
+          out[j][i] = fma(row[3], x[j][3], fma(row[2], x[j][2], fma(row[1], x[j][1], row[0] * x[j][0])));
+      }
+    };
+    // out[j] = column s of M (staged transposed: row s), all ones for a missing state
+    auto column = [&](const double* mt, const int (&s)[K], double (&out)[K][4]) {
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        LoadShared4(mt + 4 * (s[j] & 3), out[j]);
+        if (s[j] >= kStates) out[j][0] = out[j][1] = out[j][2] = out[j][3] = 1.0;
+      }
+    };
+
+    for (int chunk_begin = 0; chunk_begin < op_count; chunk_begin += kChunk) {
+      const int chunk_ops = min(kChunk, op_count - chunk_begin);
+      __syncthreads();  // every warp is done with the previous chunk
+      for (int e = threadIdx.x; e < chunk_ops * 4; e += kBlock)
+        reinterpret_cast<int4*>(s_ops)[e] = reinterpret_cast<const int4*>(ops + chunk_begin)[e];
+      // the two matrices of every op of the chunk (a thread's entry of an op does not change
+      // from pass to pass when the block covers whole ops)
+      if (kOpEntries <= kBlock) {
+        const int within = threadIdx.x % kOpEntries;
+        const int entry = within & 15, cc = (within >> 4) % CT, which = within / (16 * CT);
+        const int plain = (which * CT + cc) * kMatrixStride + entry;
+        const int transposed = (which * CT + cc) * kMatrixStride + (entry & 3) * 4 + (entry >> 2);
+        for (int o = threadIdx.x / kOpEntries; o < chunk_ops; o += kBlock / kOpEntries) {
+          const DeviceOp& op = ops[chunk_begin + o];
+          const int flags = op.flags;
+          const int matrix = which ? op.matrix2 : op.matrix1;
+          s_matrix[o * kOpMatrixDoubles + ((flags & (which ? kChild2Compact : kChild1Compact)) ? transposed : plain)] =
+              v.matrix[(static_cast<size_t>(matrix) * CT + cc) * 16 + entry];
+        }
+      } else {
+        for (int e = threadIdx.x; e < chunk_ops * kOpEntries; e += kBlock) {
+          const int entry = e & 15, cc = (e >> 4) % CT, which = (e / (16 * CT)) & 1, o = e / kOpEntries;
+          const DeviceOp& op = ops[chunk_begin + o];
+          const bool transposed = op.flags & (which ? kChild2Compact : kChild1Compact);
+          const int matrix = which ? op.matrix2 : op.matrix1;
+          s_matrix[o * kOpMatrixDoubles + (which * CT + cc) * kMatrixStride +
+                   (transposed ? (entry & 3) * 4 + (entry >> 2) : entry)] =
+              v.matrix[(static_cast<size_t>(matrix) * CT + cc) * 16 + entry];
+        }
+      }
+      __syncthreads();
+      request(s_ops[0]);  // (the first op of a chunk waits for its operands)
+      for (int o = 0; o < chunk_ops; o++) {
+        const DeviceOp& op = s_ops[o];
+        const int flags = op.flags;
+        const double* const m1 = s_matrix + o * kOpMatrixDoubles + c * kMatrixStride;
+        const double* const m2 = m1 + CT * kMatrixStride;
+        double a[K][4], b[K][4];
+        if (flags & kChild2Compact) {
+          column(m2, s2, b);
+        } else if (flags & kChild2Forward) {
+          evolve(m2, d, b);
+        } else {
+          evolve(m2, n2, b);
+        }
+        if (PRE) {
+          // a = pre o (P2 L2); child1 is the parent's pre-order partial (never compact)
+          if (flags & kChild1Forward) {
+#pragma unroll
+            for (int j = 0; j < K; j++)
+#pragma unroll
+              for (int i = 0; i < 4; i++) a[j][i] = d[j][i] * b[j][i];
+          } else {
+#pragma unroll
+            for (int j = 0; j < K; j++)
+#pragma unroll
+              for (int i = 0; i < 4; i++) a[j][i] = n1[j][i] * b[j][i];
+          }
+        } else if (flags & kChild1Compact) {
+          column(m1, s1, a);
+        } else if (flags & kChild1Forward) {
+          evolve(m1, d, a);
+        } else {
+          evolve(m1, n1, a);
+        }
+        // this op's operands are consumed: ask for the next op's
+        if (o + 1 < chunk_ops) request(s_ops[o + 1]);
+        if (PRE) {
+          // d[x] = sum_i P1[i][x] a[i]: rows of P1 scaled by a[i], added in the order i = 0..3
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            double row[4];
+            LoadShared4(m1 + 4 * i, row);
+#pragma unroll
+            for (int j = 0; j < K; j++)
+#pragma unroll
+              for (int x = 0; x < 4; x++) d[j][x] = (i == 0) ? row[x] * a[j][0] : fma(row[x], a[j][i], d[j][x]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < K; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) d[j][i] = a[j][i] * b[j][i];
+        }
+        if (op.scale_write >= 0) {
+          double largest[K];
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+            largest[j] = fmax(fmax(d[j][0], d[j][1]), fmax(d[j][2], d[j][3]));
+#pragma unroll
+            for (int s = kPerWarp; s < 32; s <<= 1) largest[j] = fmax(largest[j], __shfl_xor_sync(kFull, largest[j], s));
+            if (largest[j] == 0.0) largest[j] = 1.0;
+            const double inverse = 1.0 / largest[j];
+#pragma unroll
+            for (int i = 0; i < 4; i++) d[j][i] *= inverse;
+          }
+          if (c == 0) {
+#pragma unroll
+            for (int j = 0; j < K; j++)
+              if (active[j]) scale_at[j][op.scale_at] = largest[j];
+          }
+          if (cumulative >= 0) {
+            if (cumulative_in_register) {
+#pragma unroll
+              for (int j = 0; j < K; j++)
+                if (c == pending) held[j] = largest[j];
+              if (++pending == CT) flush_logarithms();
+            } else if (c == 0) {
+#pragma unroll
+              for (int j = 0; j < K; j++)
+                if (active[j]) scale_at[j][static_cast<int64_t>(cumulative) * v.P] += log(largest[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++)
+          if (active[j]) Store4(const_cast<double*>(partial_at[j]) + op.dest_at, d[j]);
+      }
+    }
+    if (cumulative >= 0 && cumulative_in_register) {
+      if (pending > 0) flush_logarithms();
+      if (c == 0) {
+#pragma unroll
+        for (int j = 0; j < K; j++)
+          if (active[j]) scale_at[j][static_cast<int64_t>(cumulative) * v.P] = cum[j];
+      }
     }
   }
 }
@@ -433,6 +665,8 @@ int UpdatePartials(int instance, const BeagleOperation* operations, int count, i
   if (cumulative != BEAGLE_OP_NONE && (cumulative < 0 || cumulative >= inst->scalers)) return BEAGLE_ERROR_OUT_OF_RANGE;
   SHIM_CUDA(cudaSetDevice(inst->device));
   std::vector<DeviceOp> ops(count);
+  int previous_dest = -1;
+  bool cumulative_in_register = true;  // unless an op of the list writes the cumulative buffer itself
   for (int o = 0; o < count; o++) {
     const BeagleOperation& op = operations[o];
     if (op.destinationPartials < 0 || op.destinationPartials >= inst->buffers || op.child1Partials < 0 ||
@@ -443,11 +677,32 @@ int UpdatePartials(int instance, const BeagleOperation* operations, int count, i
       return BEAGLE_ERROR_OUT_OF_RANGE;
     // (a pre-order parent partial is never a compact tip)
     if (PRE && inst->is_compact_host[op.child1Partials]) return BEAGLE_ERROR_OUT_OF_RANGE;
+    int32_t flags = 0;
+    if (inst->is_compact_host[op.child1Partials]) {
+      flags |= kChild1Compact;
+    } else if (op.child1Partials == previous_dest) {
+      flags |= kChild1Forward;
+    }
+    if (inst->is_compact_host[op.child2Partials]) {
+      flags |= kChild2Compact;
+    } else if (op.child2Partials == previous_dest) {
+      flags |= kChild2Forward;
+    }
     ops[o] = DeviceOp{op.destinationPartials, op.destinationScaleWrite < 0 ? -1 : op.destinationScaleWrite,
                       op.child1Partials,      op.child1TransitionMatrix,
-                      op.child2Partials,      op.child2TransitionMatrix};
+                      op.child2Partials,      op.child2TransitionMatrix,
+                      flags,                  0,
+                      0,                      0,
+                      0,                      0};
+    const int64_t partial = static_cast<int64_t>(inst->PartialSize());
+    ops[o].dest_at = op.destinationPartials * partial;
+    ops[o].child1_at = (flags & kChild1Compact) ? static_cast<int64_t>(op.child1Partials) * inst->P : op.child1Partials * partial;
+    ops[o].child2_at = (flags & kChild2Compact) ? static_cast<int64_t>(op.child2Partials) * inst->P : op.child2Partials * partial;
+    ops[o].scale_at = static_cast<int64_t>(std::max(op.destinationScaleWrite, 0)) * inst->P;
+    if (op.destinationScaleWrite >= 0 && op.destinationScaleWrite == cumulative) cumulative_in_register = false;
     const int status = MarkCompact(inst, op.destinationPartials, false);
     if (status != BEAGLE_SUCCESS) return status;
+    previous_dest = op.destinationPartials;
   }
   if (!inst->ops.Reserve(count)) return BEAGLE_ERROR_OUT_OF_MEMORY;
   SHIM_CUDA(cudaMemcpyAsync(inst->ops.ptr, ops.data(), count * sizeof(DeviceOp), cudaMemcpyHostToDevice, inst->stream));
@@ -455,14 +710,22 @@ int UpdatePartials(int instance, const BeagleOperation* operations, int count, i
   const int blocks = inst->PatternBlocks();
   const int cumulative_index = cumulative == BEAGLE_OP_NONE ? -1 : cumulative;
   SHIM_CUDA(cudaEventRecord(inst->begin, inst->stream));
-  // one thread per (pattern, category) when the category count divides a warp
+  // K adjacent patterns per thread (SBNB_BEAGLE_PATTERNS_PER_THREAD = 2: twice the loads in flight
+  // per thread, half the matrix reads, half the threads).
   const int64_t lane_threads = static_cast<int64_t>(inst->P) * inst->C;
-  const int lane_blocks = static_cast<int>(
-      std::max<int64_t>(1, std::min<int64_t>((lane_threads + kBlock - 1) / kBlock, static_cast<int64_t>(inst->sm_count) * 32)));
-#define SHIM_LANES(CT)                                                                                         \
-  case CT:                                                                                                     \
-    UpdatePartialsLanesKernel<PRE, CT><<<lane_blocks, kBlock, 0, inst->stream>>>(view, inst->ops.ptr, count,   \
-                                                                                 cumulative_index);            \
+  int K = 1;  // (two measured slower on the pre-order list and the same on the post-order one at 100k x 4)
+  if (const char* forced = std::getenv("SBNB_BEAGLE_PATTERNS_PER_THREAD")) K = std::atoi(forced) >= 2 ? 2 : 1;
+  const int lane_blocks =
+      static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((lane_threads + kBlock * K - 1) / (kBlock * K), 1 << 30)));
+#define SHIM_LANES(CT)                                                                                        \
+  case CT:                                                                                                    \
+    if (K == 2) {                                                                                             \
+      UpdatePartialsPipelinedKernel<PRE, CT, 2><<<lane_blocks, kBlock, 0, inst->stream>>>(                    \
+          view, inst->ops.ptr, count, cumulative_index, cumulative_in_register);                              \
+    } else {                                                                                                  \
+      UpdatePartialsPipelinedKernel<PRE, CT, 1><<<lane_blocks, kBlock, 0, inst->stream>>>(                    \
+          view, inst->ops.ptr, count, cumulative_index, cumulative_in_register);                              \
+    }                                                                                                         \
     break;
   switch (inst->C) {
     SHIM_LANES(1)

@@ -1,5 +1,4 @@
 # Development aid: the command list of one `gpurun -- 'bash tools/gpu_session.sh'` call (edited per session).
 mkdir -p gpurun_out
-timeout 1200 compute-sanitizer --tool racecheck --racecheck-report analysis python tools/sanitizer_cases_gp_beagle.py > gpurun_out/r02_sanitizer_racecheck_gp_beagle.log 2>&1; tail -3 gpurun_out/r02_sanitizer_racecheck_gp_beagle.log
-timeout 1200 compute-sanitizer --tool memcheck python tools/sanitizer_cases_gp_beagle.py > gpurun_out/r02_sanitizer_memcheck_gp_beagle.log 2>&1; tail -2 gpurun_out/r02_sanitizer_memcheck_gp_beagle.log
-(timeout 1500 python -m pytest tests -m gpu -x -q) > gpurun_out/session_pytest.log 2>&1; tail -3 gpurun_out/session_pytest.log
+(timeout 900 python -m pytest tests/test_beagle_shim.py -m gpu -x -q) > gpurun_out/s43_pytest.log 2>&1; tail -3 gpurun_out/s43_pytest.log
+for k in 1 2; do echo "K=$k"; SBNB_BEAGLE_PATTERNS_PER_THREAD=$k timeout 300 python tools/beagle_shim_bench.py | tee gpurun_out/s43_shim_K$k.json | cut -c100-900; done
