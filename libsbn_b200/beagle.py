@@ -16,7 +16,7 @@ class Beagle:
     """The BEAGLE calls of fat_beagle.cpp over one of the two libraries."""
 
     def __init__(self, path, n, P, C, use_tip_states):
-        self.lib = ctypes.CDLL(path or LIB_PATH)
+        self.lib = ctypes.CDLL(path or os.environ.get("SBNB_BEAGLE_LIBRARY") or LIB_PATH)
         self.n, self.P, self.C, self.N = n, P, C, 2 * n - 1
         partials = 3 * n - 2 + (0 if use_tip_states else n)  # fat_beagle.cpp:207-256
         self.handle = self.lib.beagleCreateInstance(n, partials, n if use_tip_states else 0, 4, P, 1, 2 * self.N, C,

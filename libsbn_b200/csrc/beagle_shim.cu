@@ -45,6 +45,13 @@ namespace {
 
 constexpr int kStates = 4;
 constexpr int kBlock = 128;
+// the pipelined partial updates: threads per CTA (the op records and matrices a CTA stages are
+// shared by more threads) and resident CTAs per SM (64 registers: 1024 threads)
+#ifndef SBNB_SHIM_PIPE_BLOCK
+#define SBNB_SHIM_PIPE_BLOCK 256
+#endif
+constexpr int kPipeBlock = SBNB_SHIM_PIPE_BLOCK;
+constexpr int kPipeMinBlocks = 1024 / kPipeBlock;
 
 struct alignas(16) DeviceOp {
   int32_t dest, scale_write, child1, matrix1, child2, matrix2;
@@ -164,15 +171,18 @@ __device__ __forceinline__ double OpTerm(const InstanceView& v, const DeviceOp& 
 //   * a record carries its buffers as element offsets, and the four states of a (pattern,
 //     category) move as one 256-bit access.
 constexpr int kMatrixStride = 18;  // doubles between the category blocks of a staged matrix
-__host__ __device__ constexpr int ChunkOps(int CT) { return CT <= 4 ? 16 : (CT == 8 ? 8 : 4); }
+#ifndef SBNB_SHIM_CHUNK
+#define SBNB_SHIM_CHUNK 32
+#endif
+__host__ __device__ constexpr int ChunkOps(int CT) { return CT <= 4 ? SBNB_SHIM_CHUNK : (CT == 8 ? SBNB_SHIM_CHUNK / 2 : SBNB_SHIM_CHUNK / 4); }
 
 template <bool PRE, int CT, int K>
-__global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipelinedKernel(const InstanceView v,
+__global__ void __launch_bounds__(kPipeBlock, K == 1 ? kPipeMinBlocks : (kPipeMinBlocks + 1) / 2) UpdatePartialsPipelinedKernel(const InstanceView v,
                                                                        const DeviceOp* __restrict__ ops, int op_count,
                                                                        int cumulative, int cumulative_in_register) {
   constexpr int kPerWarp = 32 / CT;  // pattern groups of a warp
   constexpr int kChunk = ChunkOps(CT);
-  constexpr int kBlockPatterns = (kBlock / 32) * kPerWarp * K;
+  constexpr int kPipeBlockPatterns = (kPipeBlock / 32) * kPerWarp * K;
   constexpr int kOpMatrixDoubles = 2 * CT * kMatrixStride;
   constexpr int kOpEntries = 2 * CT * 16;  // matrix entries staged per op
   constexpr unsigned kFull = 0xffffffffu;
@@ -181,20 +191,20 @@ __global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipeline
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane / kPerWarp;
   // (the trip count is the same for every thread of a block: the chunk loop has barriers)
-  for (int64_t base = static_cast<int64_t>(blockIdx.x) * kBlockPatterns; base < v.P;
-       base += static_cast<int64_t>(gridDim.x) * kBlockPatterns) {
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * kPipeBlockPatterns; base < v.P;
+       base += static_cast<int64_t>(gridDim.x) * kPipeBlockPatterns) {
     const int64_t first = base + static_cast<int64_t>(warp * kPerWarp + lane % kPerWarp) * K;
-    bool active[K];
-    const double* partial_at[K];  // this thread's (pattern, category) in partial buffer 0
-    const uint8_t* state_at[K];   // its pattern in compact buffer 0
-    double* scale_at[K];          // its pattern in scale buffer 0
+    // This thread's place in a partial buffer (doubles), in a state / scale row, and whether it
+    // stores: kept opaque to the compiler, which otherwise re-derives them from threadIdx at
+    // every op of the list (a third of the instructions of an op, measured).
+    int64_t elem[K];
+    int pattern[K], live[K];
 #pragma unroll
     for (int j = 0; j < K; j++) {
-      active[j] = first + j < v.P;
-      const int64_t k = active[j] ? first + j : v.P - 1;  // (idle slots shadow the last pattern and store nothing)
-      partial_at[j] = v.partials + (static_cast<int64_t>(c) * v.P + k) * kStates;
-      state_at[j] = v.compact + k;
-      scale_at[j] = v.scale + k;
+      live[j] = first + j < v.P;
+      pattern[j] = static_cast<int>(live[j] ? first + j : v.P - 1);  // (idle slots shadow the last pattern)
+      elem[j] = (static_cast<int64_t>(c) * v.P + pattern[j]) * kStates;
+      asm volatile("" : "+l"(elem[j]), "+r"(pattern[j]), "+r"(live[j]));
     }
     // The logarithms of the cumulative scale buffer are taken CT at a time: the pattern's
     // lanes all hold the op's maximum, the lane of category (rescaled ops so far) % CT keeps
@@ -205,7 +215,9 @@ __global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipeline
 #pragma unroll
     for (int j = 0; j < K; j++) {
       held[j] = 1.0;
-      cum[j] = (cumulative >= 0 && cumulative_in_register) ? scale_at[j][static_cast<int64_t>(cumulative) * v.P] : 0.0;
+      cum[j] = (cumulative >= 0 && cumulative_in_register)
+                   ? v.scale[static_cast<int64_t>(cumulative) * v.P + pattern[j]]
+                   : 0.0;
     }
     auto flush_logarithms = [&]() {
       double term[K];
@@ -233,17 +245,17 @@ __global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipeline
       const int flags = op.flags;
       if (flags & kChild1Compact) {
 #pragma unroll
-        for (int j = 0; j < K; j++) s1[j] = state_at[j][op.child1_at];
+        for (int j = 0; j < K; j++) s1[j] = v.compact[op.child1_at + pattern[j]];
       } else if (!(flags & kChild1Forward)) {
 #pragma unroll
-        for (int j = 0; j < K; j++) Load4(partial_at[j] + op.child1_at, n1[j]);
+        for (int j = 0; j < K; j++) Load4(v.partials + (op.child1_at + elem[j]), n1[j]);
       }
       if (flags & kChild2Compact) {
 #pragma unroll
-        for (int j = 0; j < K; j++) s2[j] = state_at[j][op.child2_at];
+        for (int j = 0; j < K; j++) s2[j] = v.compact[op.child2_at + pattern[j]];
       } else if (!(flags & kChild2Forward)) {
 #pragma unroll
-        for (int j = 0; j < K; j++) Load4(partial_at[j] + op.child2_at, n2[j]);
+        for (int j = 0; j < K; j++) Load4(v.partials + (op.child2_at + elem[j]), n2[j]);
       }
     };
     // out[j] = M x[j] (a full partial; M row-major in shared memory)
@@ -269,16 +281,16 @@ __global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipeline
     for (int chunk_begin = 0; chunk_begin < op_count; chunk_begin += kChunk) {
       const int chunk_ops = min(kChunk, op_count - chunk_begin);
       __syncthreads();  // every warp is done with the previous chunk
-      for (int e = threadIdx.x; e < chunk_ops * 4; e += kBlock)
+      for (int e = threadIdx.x; e < chunk_ops * 4; e += kPipeBlock)
         reinterpret_cast<int4*>(s_ops)[e] = reinterpret_cast<const int4*>(ops + chunk_begin)[e];
       // the two matrices of every op of the chunk (a thread's entry of an op does not change
       // from pass to pass when the block covers whole ops)
-      if (kOpEntries <= kBlock) {
+      if (kOpEntries <= kPipeBlock) {
         const int within = threadIdx.x % kOpEntries;
         const int entry = within & 15, cc = (within >> 4) % CT, which = within / (16 * CT);
         const int plain = (which * CT + cc) * kMatrixStride + entry;
         const int transposed = (which * CT + cc) * kMatrixStride + (entry & 3) * 4 + (entry >> 2);
-        for (int o = threadIdx.x / kOpEntries; o < chunk_ops; o += kBlock / kOpEntries) {
+        for (int o = threadIdx.x / kOpEntries; o < chunk_ops; o += kPipeBlock / kOpEntries) {
           const DeviceOp& op = ops[chunk_begin + o];
           const int flags = op.flags;
           const int matrix = which ? op.matrix2 : op.matrix1;
@@ -286,7 +298,7 @@ __global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipeline
               v.matrix[(static_cast<size_t>(matrix) * CT + cc) * 16 + entry];
         }
       } else {
-        for (int e = threadIdx.x; e < chunk_ops * kOpEntries; e += kBlock) {
+        for (int e = threadIdx.x; e < chunk_ops * kOpEntries; e += kPipeBlock) {
           const int entry = e & 15, cc = (e >> 4) % CT, which = (e / (16 * CT)) & 1, o = e / kOpEntries;
           const DeviceOp& op = ops[chunk_begin + o];
           const bool transposed = op.flags & (which ? kChild2Compact : kChild1Compact);
@@ -354,9 +366,15 @@ __global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipeline
           double largest[K];
 #pragma unroll
           for (int j = 0; j < K; j++) {
-            largest[j] = fmax(fmax(d[j][0], d[j][1]), fmax(d[j][2], d[j][3]));
+            // the reference's maximum: starts at 0, takes v when v > max (so never a NaN)
+            largest[j] = 0.0;
 #pragma unroll
-            for (int s = kPerWarp; s < 32; s <<= 1) largest[j] = fmax(largest[j], __shfl_xor_sync(kFull, largest[j], s));
+            for (int i = 0; i < 4; i++) largest[j] = d[j][i] > largest[j] ? d[j][i] : largest[j];
+#pragma unroll
+            for (int s = kPerWarp; s < 32; s <<= 1) {
+              const double other = __shfl_xor_sync(kFull, largest[j], s);
+              largest[j] = other > largest[j] ? other : largest[j];
+            }
             if (largest[j] == 0.0) largest[j] = 1.0;
             const double inverse = 1.0 / largest[j];
 #pragma unroll
@@ -365,7 +383,7 @@ __global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipeline
           if (c == 0) {
 #pragma unroll
             for (int j = 0; j < K; j++)
-              if (active[j]) scale_at[j][op.scale_at] = largest[j];
+              if (live[j]) v.scale[op.scale_at + pattern[j]] = largest[j];
           }
           if (cumulative >= 0) {
             if (cumulative_in_register) {
@@ -376,13 +394,13 @@ __global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipeline
             } else if (c == 0) {
 #pragma unroll
               for (int j = 0; j < K; j++)
-                if (active[j]) scale_at[j][static_cast<int64_t>(cumulative) * v.P] += log(largest[j]);
+                if (live[j]) v.scale[static_cast<int64_t>(cumulative) * v.P + pattern[j]] += log(largest[j]);
             }
           }
         }
 #pragma unroll
         for (int j = 0; j < K; j++)
-          if (active[j]) Store4(const_cast<double*>(partial_at[j]) + op.dest_at, d[j]);
+          if (live[j]) Store4(v.partials + (op.dest_at + elem[j]), d[j]);
       }
     }
     if (cumulative >= 0 && cumulative_in_register) {
@@ -390,7 +408,7 @@ __global__ void __launch_bounds__(kBlock, K == 1 ? 8 : 4) UpdatePartialsPipeline
       if (c == 0) {
 #pragma unroll
         for (int j = 0; j < K; j++)
-          if (active[j]) scale_at[j][static_cast<int64_t>(cumulative) * v.P] = cum[j];
+          if (live[j]) v.scale[static_cast<int64_t>(cumulative) * v.P + pattern[j]] = cum[j];
       }
     }
   }
@@ -498,41 +516,66 @@ __global__ void __launch_bounds__(kBlock) RootLogLikelihoodKernel(const Instance
 //   per pattern [sum_c p_c pre^T dQ_c post] / [sum_c p_c pre^T post]; a compact tip acts as its
 //   one-hot (or all-ones) partial.  Per-site values when asked, and per-block partial sums of
 //   w_k x and w_k x^2.
+//   G categories of a pattern are loaded together (2 G independent 256-bit loads in flight per
+//   thread: the kernel is a pure stream, 82 % of its stalls were on the long scoreboard with one
+//   category at a time); the differential matrices sit in shared memory.
+constexpr int kMaxStagedCategories = 16;
+template <int G>
 __global__ void __launch_bounds__(kBlock) EdgeDerivativesKernel(const InstanceView v, const int32_t* __restrict__ post,
                                                                const int32_t* __restrict__ pre,
                                                                const int32_t* __restrict__ dmatrix,
                                                                double* __restrict__ per_site,
                                                                double* __restrict__ block_sums) {
   __shared__ double smem[kBlock / 32];
+  __shared__ __align__(16) double s_dq[kMaxStagedCategories * 16];
+  __shared__ double s_weights[kMaxStagedCategories];
   const int e = blockIdx.y;
   const int post_buffer = post[e], pre_buffer = pre[e];
   const double* dq_base = v.matrix + static_cast<size_t>(dmatrix[e]) * v.C * 16;
+  const bool staged = v.C <= kMaxStagedCategories;
+  if (staged) {
+    for (int i = threadIdx.x; i < v.C * 16; i += kBlock) s_dq[i] = dq_base[i];
+    for (int i = threadIdx.x; i < v.C; i += kBlock) s_weights[i] = v.cat_weights[i];
+    __syncthreads();
+  }
+  const bool compact = v.is_compact[post_buffer];
   double sum = 0.0, sum_squares = 0.0;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < v.P; k += stride) {
     double numerator = 0.0, denominator = 0.0;
-    for (int c = 0; c < v.C; c++) {
-      double x[4], p[4];
-      if (v.is_compact[post_buffer]) {
-        const int s = v.compact[static_cast<size_t>(post_buffer) * v.P + k];
+    const int s = compact ? v.compact[static_cast<size_t>(post_buffer) * v.P + k] : 0;
+    for (int c0 = 0; c0 < v.C; c0 += G) {
+      double x[G][4], p[G][4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) x[i] = (s >= kStates || s == i) ? 1.0 : 0.0;
-      } else {
-        Load4(Partial(v, post_buffer, c, k), x);
-      }
-      Load4(Partial(v, pre_buffer, c, k), p);
-      const double* dq = dq_base + c * 16;
-      double num_c = 0.0, den_c = 0.0;
+      for (int g = 0; g < G; g++) {
+        if (compact) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        double row[4];
-        Load4(dq + i * 4, row);
-        const double dq_post = row[0] * x[0] + row[1] * x[1] + row[2] * x[2] + row[3] * x[3];
-        num_c += p[i] * dq_post;
-        den_c += p[i] * x[i];
+          for (int i = 0; i < 4; i++) x[g][i] = (s >= kStates || s == i) ? 1.0 : 0.0;
+        } else {
+          Load4(Partial(v, post_buffer, c0 + g, k), x[g]);
+        }
+        Load4(Partial(v, pre_buffer, c0 + g, k), p[g]);
       }
-      numerator += v.cat_weights[c] * num_c;
-      denominator += v.cat_weights[c] * den_c;
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const int c = c0 + g;
+        double num_c = 0.0, den_c = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          double row[4];
+          if (staged) {
+            LoadShared4(s_dq + c * 16 + i * 4, row);
+          } else {
+            Load4(dq_base + c * 16 + i * 4, row);
+          }
+          const double dq_post = row[0] * x[g][0] + row[1] * x[g][1] + row[2] * x[g][2] + row[3] * x[g][3];
+          num_c += p[g][i] * dq_post;
+          den_c += p[g][i] * x[g][i];
+        }
+        const double weight = staged ? s_weights[c] : v.cat_weights[c];
+        numerator += weight * num_c;
+        denominator += weight * den_c;
+      }
     }
     const double derivative = numerator / denominator;
     if (per_site != nullptr) per_site[static_cast<size_t>(e) * v.P + k] = derivative;
@@ -716,14 +759,14 @@ int UpdatePartials(int instance, const BeagleOperation* operations, int count, i
   int K = 1;  // (two measured slower on the pre-order list and the same on the post-order one at 100k x 4)
   if (const char* forced = std::getenv("SBNB_BEAGLE_PATTERNS_PER_THREAD")) K = std::atoi(forced) >= 2 ? 2 : 1;
   const int lane_blocks =
-      static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((lane_threads + kBlock * K - 1) / (kBlock * K), 1 << 30)));
+      static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((lane_threads + kPipeBlock * K - 1) / (kPipeBlock * K), 1 << 30)));
 #define SHIM_LANES(CT)                                                                                        \
   case CT:                                                                                                    \
     if (K == 2) {                                                                                             \
-      UpdatePartialsPipelinedKernel<PRE, CT, 2><<<lane_blocks, kBlock, 0, inst->stream>>>(                    \
+      UpdatePartialsPipelinedKernel<PRE, CT, 2><<<lane_blocks, kPipeBlock, 0, inst->stream>>>(                    \
           view, inst->ops.ptr, count, cumulative_index, cumulative_in_register);                              \
     } else {                                                                                                  \
-      UpdatePartialsPipelinedKernel<PRE, CT, 1><<<lane_blocks, kBlock, 0, inst->stream>>>(                    \
+      UpdatePartialsPipelinedKernel<PRE, CT, 1><<<lane_blocks, kPipeBlock, 0, inst->stream>>>(                    \
           view, inst->ops.ptr, count, cumulative_index, cumulative_in_register);                              \
     }                                                                                                         \
     break;
@@ -1012,10 +1055,26 @@ int beagleCalculateEdgeDerivatives(int instance, const int* postBufferIndices, c
                             inst->stream));
   double* per_site = outDerivatives ? inst->out.ptr + 2 * static_cast<size_t>(count) : nullptr;
   SHIM_CUDA(cudaEventRecord(inst->begin, inst->stream));
-  EdgeDerivativesKernel<<<dim3(blocks, count), kBlock, 0, inst->stream>>>(inst->View(), inst->indices.ptr,
+  const dim3 derivative_grid(blocks, count);
+#ifndef SBNB_SHIM_DERIV_G
+#define SBNB_SHIM_DERIV_G 1  // (categories loaded together: 2 and 4 measured 4 % and 27 % SLOWER at 100k x 4 -- more concurrent DRAM streams)
+#endif
+  if (inst->C % 4 == 0 && SBNB_SHIM_DERIV_G >= 4) {
+    EdgeDerivativesKernel<4><<<derivative_grid, kBlock, 0, inst->stream>>>(inst->View(), inst->indices.ptr,
                                                                           inst->indices.ptr + count,
                                                                           inst->indices.ptr + 2 * count, per_site,
                                                                           inst->sums.ptr);
+  } else if (inst->C % 2 == 0 && SBNB_SHIM_DERIV_G >= 2) {
+    EdgeDerivativesKernel<2><<<derivative_grid, kBlock, 0, inst->stream>>>(inst->View(), inst->indices.ptr,
+                                                                          inst->indices.ptr + count,
+                                                                          inst->indices.ptr + 2 * count, per_site,
+                                                                          inst->sums.ptr);
+  } else {
+    EdgeDerivativesKernel<1><<<derivative_grid, kBlock, 0, inst->stream>>>(inst->View(), inst->indices.ptr,
+                                                                          inst->indices.ptr + count,
+                                                                          inst->indices.ptr + 2 * count, per_site,
+                                                                          inst->sums.ptr);
+  }
   SHIM_CUDA(cudaGetLastError());
   SumBlocksKernel<<<(2 * count + 127) / 128, 128, 0, inst->stream>>>(inst->sums.ptr, blocks, 2, count, inst->out.ptr);
   SHIM_CUDA(cudaGetLastError());

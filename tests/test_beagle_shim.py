@@ -88,3 +88,69 @@ def test_reference_doctest_suite_passes_over_the_device_beagle_library():
     with open(integration._artefact("doctest_beagle"), "rb") as handle:
         binary = handle.read()
     assert b"beagleUpdatePrePartials" in binary  # the reference's FatBeagle is what runs
+
+
+def _depth_first(post, n):
+    """The same ops, children before parents in depth-first order (libsbn's traversal order: the
+    destination of an op is a child of the next one, which the device kernel keeps in registers)."""
+    by_dest = {int(op[0]): op for op in post}
+    order = []
+
+    def visit(v):
+        if v < n:
+            return
+        visit(int(by_dest[v][3]))
+        visit(int(by_dest[v][5]))
+        order.append(by_dest[v])
+
+    visit(int(post[-1][0]))
+    return np.array(order, dtype=np.int32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("categories,variant", [(4, "depth_first"), (4, "cumulative_is_written"), (2, "depth_first"),
+                                                (8, "depth_first"), (1, "both_children_forwarded")])
+def test_partial_update_op_lists_the_pipelined_kernel_special_cases(categories, variant):
+    """Op lists longer than one staged chunk, in depth-first order (register forwarding at nearly every
+    op), with an op whose scale buffer IS the cumulative buffer (the sums then go through memory), and
+    with an op whose two children are both the previous destination: root log likelihoods through the
+    device library and the CPU restatement."""
+    rng = np.random.default_rng(categories * 7 + len(variant))
+    n, P = 41, 515
+    states = rng.integers(0, 4, size=(n, P)).astype(np.int32)
+    states[rng.random(states.shape) < 0.05] = 4
+    weights = rng.integers(1, 4, size=P).astype(np.float64)
+    post, _ = random_tree_operations(n, rng, True)
+    post = _depth_first(post, n)
+    assert len(post) == n - 1 > 32
+    if variant == "cumulative_is_written":
+        post[5][1] = 0
+    if variant == "both_children_forwarded":
+        post[7][3] = post[7][5] = post[6][0]
+        post[7][4] = post[7][6] = post[6][0]
+    lengths = rng.exponential(0.1, size=2 * n - 1)
+    evec, ivec, evals, freqs, q = gtr_eigensystem()
+    rates = np.sort(rng.gamma(2.0, 0.5, size=categories))
+    rates /= rates.mean()
+    values = []
+    for path in (SHIM, ORACLE):
+        beagle = Beagle(path, n, P, categories, True)
+        beagle.set_tips(states, weights, True)
+        beagle.set_model(evec, ivec, evals, freqs, rates, np.full(categories, 1.0 / categories))
+        keep_i, idx = beagle._i(np.arange(2 * n - 2))
+        keep_l, lens = beagle._d(lengths[:2 * n - 2])
+        beagle.ok(beagle.lib.beagleUpdateTransitionMatrices(beagle.handle, 0, idx, None, None, lens, 2 * n - 2))
+        for repeat in range(2):  # (the second call adds onto the cumulative buffer the first one left)
+            if repeat == 0:
+                beagle.ok(beagle.lib.beagleResetScaleFactors(beagle.handle, 0))
+            keep_a, ops = beagle._i(post)
+            beagle.ok(beagle.lib.beagleUpdatePartials(beagle.handle, ops, len(post), 0))
+            keep_r, root = beagle._i([2 * n - 2])
+            keep_z, zero = beagle._i([0])
+            logl = ctypes.c_double()
+            beagle.ok(beagle.lib.beagleCalculateRootLogLikelihoods(beagle.handle, root, zero, zero, zero, 1,
+                                                                   ctypes.byref(logl)))
+            values.append(logl.value)
+        beagle.close()
+    assert np.all(np.isfinite(values))
+    np.testing.assert_allclose(values[:2], values[2:], rtol=1e-13)

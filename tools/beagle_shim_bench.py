@@ -79,14 +79,23 @@ def measure(n=100, P=100000, C=4, repeats=5, device=None):
                 "root pre-order partial uploaded as fat_beagle.cpp:316-325 does) and a stream synchronisation per call",
         "log_likelihood": logl,
     }
+    # Two fractions per call.  `algorithmic_frac_of_peak`: SURVEY.md 8d's bytes (every partial through HBM)
+    # over the time -- it exceeds 1 where the 126 MB L2 serves partials written a few ops earlier.
+    # `hbm_frac`: the DRAM bytes ncu measured for the same launch at this size (profiles/
+    # r02_beagle_shim_ncu_summary.json, committed with the kernels) over the time = real HBM utilisation.
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks):
-        hbm = json.load(open(peaks)).get("hbm_gbs")
-        if hbm:
-            out["hbm_peak_GBps_measured"] = hbm
-            out["update_partials"]["frac_of_peak"] = out["update_partials"]["GBps"] / hbm
-            out["update_pre_partials"]["frac_of_peak"] = out["update_pre_partials"]["GBps"] / hbm
-            out["edge_derivatives"]["frac_of_peak"] = out["edge_derivatives"]["GBps"] / hbm
+    hbm = json.load(open(peaks)).get("hbm_gbs") if os.path.exists(peaks) else None
+    summary_path = os.path.join(ROOT, "profiles", "r02_beagle_shim_ncu_summary.json")
+    measured = json.load(open(summary_path))["kernels"] if os.path.exists(summary_path) else {}
+    same_size = (n, P, C) == (100, 100000, 4)
+    if hbm:
+        out["hbm_peak_GBps_measured"] = hbm
+        for key in ("update_partials", "update_pre_partials", "edge_derivatives"):
+            out[key]["algorithmic_frac_of_peak"] = out[key]["GBps"] / hbm
+            if same_size and key in measured:
+                out[key]["dram_GB_measured"] = measured[key]["dram_bytes"] / 1e9
+                out[key]["hbm_GBps"] = measured[key]["dram_bytes"] / out[key]["ms"] / 1e6
+                out[key]["hbm_frac"] = out[key]["hbm_GBps"] / hbm
     beagle.close()
     return out
 
