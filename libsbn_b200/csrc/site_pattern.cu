@@ -123,27 +123,32 @@ __global__ void __launch_bounds__(kHashThreads) HashKernel(
   }
   uint32_t seen = 0;  // OR of the packed words: bit 3 of a field = an unknown character
   const uint8_t* column = sequences + site0;
-  for (int t0 = 0; t0 < taxon_count; t0 += 8) {
-    // (a thread has one 4-byte load per taxon, so the loads of several taxa must be in
-    //  flight together to cover the HBM latency)
-    uint32_t word[8];
+  for (int t0 = 0; t0 < taxon_count; t0 += 16) {
+    // (a thread has one 4-byte load per taxon, so the loads of many taxa must be in flight
+    //  together to cover the HBM latency: 16 measured 0.31 ms against 0.37 ms with 8 at
+    //  1000 taxa x 1M sites)
+    uint32_t word[16];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 16; i++)
       word[i] = (t0 + i < taxon_count) ? *reinterpret_cast<const uint32_t*>(column + static_cast<int64_t>(t0 + i) * pitch)
                                        : 0x41414141u;  // (rows past the last taxon read as 'A' for every site)
-    uint32_t packed[kSitesPerThread];
 #pragma unroll
-    for (int k = 0; k < kSitesPerThread; k++) packed[k] = 0;
+    for (int half = 0; half < 2; half++) {
+      if (t0 + 8 * half >= taxon_count) break;  // (same number of hash steps for every site)
+      uint32_t packed[kSitesPerThread];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+      for (int k = 0; k < kSitesPerThread; k++) packed[k] = 0;
 #pragma unroll
-      for (int k = 0; k < kSitesPerThread; k++) packed[k] |= shifted[i][(word[i] >> (8 * k)) & 0xffu];
-    }
+      for (int i = 0; i < 8; i++) {
 #pragma unroll
-    for (int k = 0; k < kSitesPerThread; k++) {
-      seen |= packed[k];
-      ha[k] = HashStep(ha[k], packed[k], 0xcc9e2d51u, 0x1b873593u, 15, 13, 5u, 0xe6546b64u);  // (MurmurHash3's own)
-      hb[k] = HashStep(hb[k], packed[k], 0x85ebca6bu, 0xc2b2ae35u, 16, 11, 9u, 0x7f4a7c15u);
+        for (int k = 0; k < kSitesPerThread; k++) packed[k] |= shifted[i][(word[8 * half + i] >> (8 * k)) & 0xffu];
+      }
+#pragma unroll
+      for (int k = 0; k < kSitesPerThread; k++) {
+        seen |= packed[k];
+        ha[k] = HashStep(ha[k], packed[k], 0xcc9e2d51u, 0x1b873593u, 15, 13, 5u, 0xe6546b64u);  // (MurmurHash3's own)
+        hb[k] = HashStep(hb[k], packed[k], 0x85ebca6bu, 0xc2b2ae35u, 16, 11, 9u, 0x7f4a7c15u);
+      }
     }
   }
   if (seen & 0x88888888u) {
