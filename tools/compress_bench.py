@@ -1,5 +1,5 @@
 """Site-pattern compression (sbnb_compress_site_patterns) on synthetic alignments:
-device time (CUDA events around the five kernels), algorithmic bytes
+device time (CUDA events around the kernel sequence), algorithmic bytes
 (read taxa x sites characters, write taxa x patterns symbols + 8 bytes per weight)
 over that time against the measured HBM peak, the end-to-end call (host buffers,
 H2D/D2H inside), and the UNMODIFIED reference's SitePattern::Compress
