@@ -95,21 +95,60 @@ class Beagle:
         self.ok(self.lib.beagleFinalizeInstance(self.handle))
 
 
-def random_tree_operations(n, rng, rescaling):
-    """A random rooted binary tree in libsbn's numbering (leaves 0..n-1, internal nodes in post-order,
-    root 2n-2) as the op lists of fat_beagle.cpp:327-362."""
+def random_tree_operations(n, rng, rescaling, order="libsbn"):
+    """A random rooted binary tree as the op lists of fat_beagle.cpp:327-362.
+
+    order = "libsbn": libsbn's numbering AND order -- leaves 0..n-1, internal nodes numbered by a depth-first
+    post-order traversal (root 2n-2); the post-order list in that traversal's order (Node::Postorder,
+    node.cpp:205-211), the pre-order list as Node::TriplePreorderBifurcating emits it (node.cpp:226-261:
+    a node's first child, that child's subtree, then its second child and its subtree).
+    order = "node_id": internal nodes numbered in the order of the random joins and the lists in id order
+    (children before parents, but not depth-first: consecutive ops are rarely parent and child)."""
     N = 2 * n - 1
-    roots, children, next_id = list(range(n)), {}, n
+    roots, joined, next_id = list(range(n)), {}, n
     while len(roots) > 1:
         a, b = (roots.pop(int(rng.integers(len(roots)))) for _ in range(2))
-        children[next_id] = (a, b)
+        joined[next_id] = (a, b)
         roots.append(next_id)
         next_id += 1
-    post = [[v, (v - n + 1) if rescaling else OP_NONE, OP_NONE, a, a, b, b] for v, (a, b) in sorted(children.items())]
-    pre = []
-    for v in sorted(children, reverse=True):  # parents before children
-        for child, sister in (children[v], children[v][::-1]):
-            pre.append([child + N, (child + 1 + n - 1) if rescaling else OP_NONE, OP_NONE, v + N, child, sister, sister])
+    if order == "node_id":
+        children = joined
+        post_order = sorted(children)
+        pre_pairs = [(v, child, sister) for v in sorted(children, reverse=True)
+                     for child, sister in (children[v], children[v][::-1])]
+    else:
+        # renumber the internal nodes by a depth-first post-order traversal
+        new_id, visit_order, stack = {t: t for t in range(n)}, [], [(next_id - 1, False)]
+        while stack:
+            v, expanded = stack.pop()
+            if v < n:
+                continue
+            if expanded:
+                new_id[v] = n + len(visit_order)
+                visit_order.append(v)
+            else:
+                stack.append((v, True))
+                stack.append((joined[v][1], False))
+                stack.append((joined[v][0], False))
+        children = {new_id[v]: (new_id[joined[v][0]], new_id[joined[v][1]]) for v in visit_order}
+        post_order = sorted(children)
+        pre_pairs, stack = [], [(N - 1, False)]
+        while stack:  # Node::TriplePreorderBifurcating
+            v, visited = stack.pop()
+            c0, c1 = children[v]
+            if visited:
+                pre_pairs.append((v, c1, c0))
+                if c1 >= n:
+                    stack.append((c1, False))
+            else:
+                pre_pairs.append((v, c0, c1))
+                stack.append((v, True))
+                if c0 >= n:
+                    stack.append((c0, False))
+    post = [[v, (v - n + 1) if rescaling else OP_NONE, OP_NONE, children[v][0], children[v][0], children[v][1],
+             children[v][1]] for v in post_order]
+    pre = [[child + N, (child + 1 + n - 1) if rescaling else OP_NONE, OP_NONE, v + N, child, sister, sister]
+           for v, child, sister in pre_pairs]
     return np.array(post, dtype=np.int32), np.array(pre, dtype=np.int32)
 
 

@@ -49,15 +49,16 @@ def test_no_device_means_no_resource_not_a_cpu_fallback():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("order", ["libsbn", "node_id"])
 @pytest.mark.parametrize("categories,use_tip_states,rescaling", [(1, True, False), (4, True, True), (4, False, False),
                                                                  (3, True, True), (4, True, False)])
-def test_device_library_against_the_cpu_restatement(categories, use_tip_states, rescaling):
+def test_device_library_against_the_cpu_restatement(categories, use_tip_states, rescaling, order):
     rng = np.random.default_rng(categories * 10 + use_tip_states * 2 + rescaling)
     n, P = 13, 1003
     states = rng.integers(0, 4, size=(n, P)).astype(np.int32)
     states[rng.random(states.shape) < 0.05] = 4
     weights = rng.integers(1, 6, size=P).astype(np.float64)
-    post, pre = random_tree_operations(n, rng, rescaling)
+    post, pre = random_tree_operations(n, rng, rescaling, order)
     lengths = rng.exponential(0.1, size=2 * n - 1)
     evec, ivec, evals, freqs, q = gtr_eigensystem()
     rates = np.sort(rng.gamma(2.0, 0.5, size=categories))
@@ -120,7 +121,7 @@ def test_partial_update_op_lists_the_pipelined_kernel_special_cases(categories, 
     states = rng.integers(0, 4, size=(n, P)).astype(np.int32)
     states[rng.random(states.shape) < 0.05] = 4
     weights = rng.integers(1, 4, size=P).astype(np.float64)
-    post, _ = random_tree_operations(n, rng, True)
+    post, _ = random_tree_operations(n, rng, True, "node_id")
     post = _depth_first(post, n)
     assert len(post) == n - 1 > 32
     if variant == "cumulative_is_written":

@@ -22,12 +22,23 @@ from libsbn_b200 import beagle as harness  # noqa: E402  (the BEAGLE call sequen
 
 
 def measure(n=100, P=100000, C=4, repeats=5, device=None):
+    """The op lists in libsbn's own order (depth-first: the reference's call sequence), and as
+    `node_id_order` the same measurement with the internal nodes numbered by random joins and the lists in
+    id order (consecutive ops rarely parent and child: no operand stays in registers)."""
     if device is not None:
         os.environ["SBNB_BEAGLE_DEVICE"] = str(device)
+    out = _measure(n, P, C, repeats, "libsbn")
+    other = _measure(n, P, C, repeats, "node_id")
+    out["node_id_order"] = {key: other[key] for key in ("update_partials", "update_pre_partials", "edge_derivatives",
+                                                        "device_ms_per_logl_plus_gradient")}
+    return out
+
+
+def _measure(n, P, C, repeats, order):
     rng = np.random.default_rng(20261017)
     states = rng.integers(0, 4, size=(n, P)).astype(np.int32)
     states[rng.random(states.shape) < 0.01] = 4
-    post, pre = harness.random_tree_operations(n, rng, True)
+    post, pre = harness.random_tree_operations(n, rng, True, order)
     lengths = np.maximum(rng.exponential(0.1, size=2 * n - 1), 1e-6)
     evec, ivec, evals, freqs, q = harness.gtr_eigensystem()
     rates = np.array([0.03, 0.25, 0.8, 2.92])[:C] if C == 4 else np.ones(C)
@@ -65,7 +76,8 @@ def measure(n=100, P=100000, C=4, repeats=5, device=None):
     # post-order writes n-1, reads n-2 partials; pre-order writes 2n-2, reads (2n-4) + (n-2)
     post_bytes, pre_bytes = (2 * n - 3) * U, (5 * n - 8) * U
     out = {
-        "workload": f"BEAGLE-compatible device library, one tree: {n} taxa x {P} patterns x {C} categories, GTR, rescaling on",
+        "workload": f"BEAGLE-compatible device library, one tree: {n} taxa x {P} patterns x {C} categories, GTR, rescaling on, "
+                    "op lists in libsbn's (depth-first) order",
         "partial_bytes_U": U,
         "update_partials": {"ms": med["post_ms"], "algorithmic_GB": post_bytes / 1e9,
                             "GBps": post_bytes / med["post_ms"] / 1e6},
@@ -86,7 +98,7 @@ def measure(n=100, P=100000, C=4, repeats=5, device=None):
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm = json.load(open(peaks)).get("hbm_gbs") if os.path.exists(peaks) else None
     summary_path = os.path.join(ROOT, "profiles", "r02_beagle_shim_ncu_summary.json")
-    measured = json.load(open(summary_path))["kernels"] if os.path.exists(summary_path) else {}
+    measured = json.load(open(summary_path)).get("kernels_" + order, {}) if os.path.exists(summary_path) else {}
     same_size = (n, P, C) == (100, 100000, 4)
     if hbm:
         out["hbm_peak_GBps_measured"] = hbm
