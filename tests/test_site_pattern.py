@@ -100,6 +100,9 @@ def test_device_matches_the_restatement(restatement, taxa, sites, distinct):
     assert got.weights.sum() == sites
     again = SitePattern(sequences)  # deterministic
     assert np.array_equal(again.patterns, got.patterns) and np.array_equal(again.weights, got.weights)
+    # the characters as one [taxon][site] array (no host copy)
+    array = SitePattern(np.array([np.frombuffer(s, np.uint8) for s in sequences]))
+    assert np.array_equal(array.patterns, got.patterns) and np.array_equal(array.weights, got.weights)
 
 
 @pytest.mark.gpu

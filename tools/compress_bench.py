@@ -25,9 +25,9 @@ def alignment(taxa, sites, distinct, seed):
     if distinct is None:  # iid columns (BASELINE configs[3], [4]): 1 % gaps
         states = rng.integers(0, 4, size=(taxa, sites), dtype=np.uint8)
         states[rng.integers(0, 100, size=(taxa, sites), dtype=np.uint8) == 0] = 4
-        return [bytes(row) for row in alphabet[states]]
+        return np.ascontiguousarray(alphabet[states])
     pool = alphabet[rng.integers(0, 5, size=(taxa, distinct))]
-    return [bytes(row) for row in pool[:, rng.integers(0, distinct, size=sites)]]
+    return np.ascontiguousarray(pool[:, rng.integers(0, distinct, size=sites)])
 
 
 def main():
@@ -60,7 +60,7 @@ def main():
             sample = min(sites, 100000)
             with tempfile.NamedTemporaryFile("w", suffix=".fasta", delete=False) as handle:
                 for t, row in enumerate(sequences):
-                    handle.write(f">t{t:04d}\n{row[:sample].decode()}\n")
+                    handle.write(f">t{t:04d}\n{bytes(row[:sample]).decode()}\n")
             start = time.perf_counter()
             subprocess.run([dump, handle.name], stdout=subprocess.DEVNULL, check=True)
             seconds = time.perf_counter() - start
