@@ -1,3 +1,3 @@
+# Development aid: the command list of one `gpurun -- 'bash tools/gpu_session.sh'` call (edited per session).
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_site_pattern.py tests/test_integration_gpu.py -m gpu -x -q) > gpurun_out/s57_pytest.log 2>&1; tail -3 gpurun_out/s57_pytest.log
-timeout 900 python tools/compress_bench.py 2>&1 | tee gpurun_out/r02_compress_bench.jsonl | cut -c1-420
+(time python bench.py > gpurun_out/s58_bench.json) 2> gpurun_out/s58_bench.err; tail -4 gpurun_out/s58_bench.err; cut -c1-300 gpurun_out/s58_bench.json
