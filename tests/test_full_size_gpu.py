@@ -8,7 +8,9 @@ boundaries and chunking are the full-size ones).
   * logL and every gradient are linear in the pattern weights (x2 is bit-exact);
   * a permutation of the patterns only reorders the sums;
   * d logL / d t agrees with central differences of logL;
-  * power-of-two rescaling does not change the result.
+  * power-of-two rescaling does not change the result;
+  * the fused tree walk and BEAGLE's op-at-a-time schedule on the device (two implementations
+    that share no kernel) agree on one tree at full size.
 """
 import numpy as np
 import pytest
@@ -159,3 +161,54 @@ def test_config5_shard_properties(oracle):
     engine.set_pattern_range(begin, end)
     ranged = raw(engine, batch, params)
     assert close(ranged[0][:1], want["log_likelihood"], 1e-10)
+
+
+@pytest.mark.parametrize("taxa,patterns", [(100, 100000), (1000, 20000)])
+def test_the_fused_walk_and_the_beagle_compatible_library_agree_at_full_size(taxa, patterns):
+    """Two independent device implementations on one tree at BASELINE configs[3] size (100 taxa x 100k
+    patterns, GTR + Weibull 4, rescaling on) and on a 1000-taxon tree (configs[4]'s depth, where both
+    rescale at nearly every node): the fused tree walk behind the C ABI, and BEAGLE's
+    op-at-a-time schedule through libhmsbeagle_b200.so driven by FatBeagle's call sequence
+    (fat_beagle.cpp:119-175) in libsbn's op order.  Log likelihood 1e-10, every edge derivative 1e-8.
+    (The unrooted gradient of a bifurcating tree slides the root, tree.cpp:72-78: the first root child
+    carries the derivative of the merged edge, which for a reversible model is the derivative of either
+    root edge of the unslid tree.)"""
+    from libsbn_b200 import beagle
+    categories, shape = 4, 0.5
+    N = 2 * taxa - 1
+    rng = np.random.default_rng(20261018)
+    states = alignment(taxa, patterns, 77)
+    weights = rng.integers(1, 4, size=patterns).astype(np.float64)
+    post, pre = beagle.random_tree_operations(taxa, rng, True)
+    parent_ids = np.full(N - 1, -1, dtype=np.int32)
+    for op in post:
+        parent_ids[op[3]] = parent_ids[op[5]] = op[0]
+    lengths = np.maximum(rng.exponential(0.1, size=N), 1e-6)
+    lengths[N - 1] = 0.0
+    # the library side: GTR eigensystem and Weibull rates (site_model.cpp:37-62) handed to BEAGLE
+    evec, ivec, evals, freqs, q = beagle.gtr_eigensystem()
+    quantiles = (2.0 * np.arange(categories) + 1.0) / (2.0 * categories)
+    rates = (-np.log(1.0 - quantiles)) ** (1.0 / shape)
+    rates /= rates.mean()
+    library = beagle.Beagle(None, taxa, patterns, categories, True)
+    library.set_tips(states.astype(np.int32), weights, True)
+    library.set_model(evec, ivec, evals, freqs, rates, np.full(categories, 1.0 / categories))
+    logl, sums, _, _ = library.log_likelihood_and_gradient(post, pre, lengths, q, rates, freqs, True)
+    library.close()
+    # the fused walk
+    spec = sbn.PhyloModelSpecification("GTR", "weibull+4", "none")
+    engine = sbn.Engine(spec, states, weights)
+    batch = sbn.TreeBatch(parent_ids[None, :], lengths[None, :])
+    params = GTR_ROW[None, :].copy()
+    params[0, 10] = shape
+    walk = engine.gradients(batch, params, True, substitution_gradient=False)[0]
+    assert abs(walk.log_likelihood - logl) <= 1e-10 * abs(logl)
+    gradient = walk.gradient["branch_lengths"]
+    root_children = [int(post[-1][3]), int(post[-1][5])]
+    others = np.array([e for e in range(N - 1) if e not in root_children])
+    scale = np.max(np.abs(sums))
+    assert np.max(np.abs(gradient[others] - sums[others])) <= 1e-8 * scale
+    slid = gradient[root_children]
+    carried = slid[np.argmax(np.abs(slid))]  # (the other root child is fixed at length 0: derivative reported 0)
+    assert np.min(np.abs(slid)) == 0.0
+    assert abs(carried - sums[root_children[0]]) <= 1e-8 * scale and abs(carried - sums[root_children[1]]) <= 1e-8 * scale
