@@ -57,8 +57,10 @@ class Beagle:
         self.ok(self.lib.beagleSetCategoryWeights(self.handle, 0, keeps[5][1]))
         self.ok(self.lib.beagleSetCategoryRates(self.handle, keeps[4][1]))
 
-    def log_likelihood_and_gradient(self, post_ops, pre_ops, lengths, q, rates, freqs, rescaling):
-        """FatBeagle::BranchGradientInternals (fat_beagle.cpp:119-175)."""
+    def log_likelihood_and_gradient(self, post_ops, pre_ops, lengths, q, rates, freqs, rescaling, per_site=True):
+        """FatBeagle::BranchGradientInternals (fat_beagle.cpp:119-175).  per_site=False asks for what
+        FatBeagle asks for (the sums only: fat_beagle.cpp:157-166 passes NULL for the per-site
+        derivatives and the sums of squares); the default also fetches those two, for the tests."""
         n, N = self.n, self.N
         keep_i, idx = self._i(np.arange(N - 1))
         keep_l, lens = self._d(lengths[:N - 1])
@@ -81,15 +83,16 @@ class Beagle:
         keep_3, dm_idx = self._i(np.full(N - 1, N - 1))
         keep_4, zero = self._i([0])
         sums, squares = np.zeros(N - 1), np.zeros(N - 1)
-        per_site = np.zeros((N - 1, self.P))
-        self.ok(self.lib.beagleCalculateEdgeDerivatives(self.handle, post_idx, pre_idx, dm_idx, zero, N - 1,
-                                                        per_site.ctypes.data_as(_D), sums.ctypes.data_as(_D),
-                                                        squares.ctypes.data_as(_D)))
+        per_site_values = np.zeros((N - 1, self.P)) if per_site else None
+        self.ok(self.lib.beagleCalculateEdgeDerivatives(
+            self.handle, post_idx, pre_idx, dm_idx, zero, N - 1,
+            per_site_values.ctypes.data_as(_D) if per_site else None, sums.ctypes.data_as(_D),
+            squares.ctypes.data_as(_D) if per_site else None))
         keep_5, root = self._i([N - 1])
         keep_6, cum = self._i([cumulative])
         logl = ctypes.c_double()
         self.ok(self.lib.beagleCalculateRootLogLikelihoods(self.handle, root, zero, zero, cum, 1, ctypes.byref(logl)))
-        return logl.value, sums, squares, per_site
+        return logl.value, sums, squares, per_site_values
 
     def close(self):
         self.ok(self.lib.beagleFinalizeInstance(self.handle))

@@ -193,7 +193,7 @@ def test_the_fused_walk_and_the_beagle_compatible_library_agree_at_full_size(tax
     library = beagle.Beagle(None, taxa, patterns, categories, True)
     library.set_tips(states.astype(np.int32), weights, True)
     library.set_model(evec, ivec, evals, freqs, rates, np.full(categories, 1.0 / categories))
-    logl, sums, _, _ = library.log_likelihood_and_gradient(post, pre, lengths, q, rates, freqs, True)
+    logl, sums, _, _ = library.log_likelihood_and_gradient(post, pre, lengths, q, rates, freqs, True, per_site=False)
     library.close()
     # the fused walk
     spec = sbn.PhyloModelSpecification("GTR", "weibull+4", "none")

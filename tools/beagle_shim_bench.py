@@ -67,7 +67,7 @@ def _measure(n, P, C, repeats, order):
     results = {"post_ms": [], "pre_ms": [], "derivatives_ms": [], "call_sequence_ms": []}
     for _ in range(repeats + 1):
         t0 = time.perf_counter()
-        logl, sums, _, _ = beagle.log_likelihood_and_gradient(post, pre, lengths, q, rates, freqs, True)
+        logl, sums, _, _ = beagle.log_likelihood_and_gradient(post, pre, lengths, q, rates, freqs, True, per_site=False)
         results["call_sequence_ms"].append((time.perf_counter() - t0) * 1e3)
         results["post_ms"].append(timed(lambda: beagle.ok(beagle.lib.beagleUpdatePartials(beagle.handle, post_ptr, len(post), 0))))
         results["derivatives_ms"].append(timed(derivatives))
@@ -87,8 +87,9 @@ def _measure(n, P, C, repeats, order):
                              "GBps": (3 * n - 4) * U / med["derivatives_ms"] / 1e6},
         "device_ms_per_logl_plus_gradient": med["post_ms"] + med["pre_ms"] + med["derivatives_ms"],
         "branch_gradient_call_sequence_ms": med["call_sequence_ms"],
-        "note": "call_sequence includes the host <-> device copies of the BEAGLE API (per-site derivatives, a U-sized "
-                "root pre-order partial uploaded as fat_beagle.cpp:316-325 does) and a stream synchronisation per call",
+        "note": "call_sequence = FatBeagle's calls with FatBeagle's arguments (sums of derivatives only), including the "
+                "host <-> device copies of the BEAGLE API (a U-sized root pre-order partial built and uploaded as "
+                "fat_beagle.cpp:316-325 does) and a stream synchronisation per call",
         "log_likelihood": logl,
     }
     # Two fractions per call.  `algorithmic_frac_of_peak`: SURVEY.md 8d's bytes (every partial through HBM)
