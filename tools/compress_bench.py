@@ -33,12 +33,13 @@ def alignment(taxa, sites, distinct, seed):
 def main():
     # (development: `--quick` skips the CPU arm and the small workload)
     quick = "--quick" in sys.argv
+    only_repeats = "--only-repeats" in sys.argv  # (profiling: just the 50k-pattern workload)
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peaks))["hbm_gbs"] if os.path.exists(peaks) else 6650.0
     for name, taxa, sites, distinct in [("100 taxa x 100k sites, iid columns", 100, 100000, None),
                                         ("1000 taxa x 1M sites, iid columns", 1000, 1000000, None),
                                         ("1000 taxa x 1M sites, 50k distinct columns", 1000, 1000000, 50000)]:
-        if quick and sites < 1000000:
+        if (quick and sites < 1000000) or (only_repeats and distinct is None):
             continue
         sequences = alignment(taxa, sites, distinct, seed=5)
         SitePattern(sequences)  # warm-up (context, allocations)
@@ -56,7 +57,7 @@ def main():
                 "frac_of_hbm_peak": algorithmic / (ms * 1e-3) / 1e9 / peak, "hbm_peak_GBps": peak,
                 "e2e_s_host_buffers": min(wall), "sites_per_s_e2e": sites / min(wall)}
         dump = os.path.join(ROOT, "oracle", "_ref", "site_pattern_dump")
-        if os.path.exists(dump) and not quick:
+        if os.path.exists(dump) and not quick and not only_repeats:
             sample = min(sites, 100000)
             with tempfile.NamedTemporaryFile("w", suffix=".fasta", delete=False) as handle:
                 for t, row in enumerate(sequences):
