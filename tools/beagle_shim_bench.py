@@ -34,7 +34,39 @@ def measure(n=100, P=100000, C=4, repeats=5, device=None):
     return out
 
 
-def _measure(n, P, C, repeats, order):
+def measure_dram(n, P, C, order):
+    """DRAM bytes of the three kernels of ONE call sequence, by ncu on a probe process (two metrics, one pass;
+    whatever the probe process prints is discarded).  ({call: bytes}, source) or (None, None)."""
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        log = os.path.join(tmp, "dram.csv")
+        command = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+                   "--print-units", "base", "--kernel-name-base", "demangled", "-k",
+                   "regex:UpdatePartialsPipelinedKernel|EdgeDerivativesKernel", "-c", "3", "--csv", "--log-file", log,
+                   sys.executable, os.path.abspath(__file__), "--_probe", order, "--taxa", str(n), "--patterns", str(P),
+                   "--categories", str(C)]
+        try:
+            subprocess.run(command, capture_output=True, text=True, timeout=600, cwd=ROOT)
+            totals = {}
+            for row in open(log):
+                cells = [c.strip('"') for c in row.strip().split('","')]
+                if len(cells) > 3 and cells[-3].startswith("dram__bytes_"):
+                    name = next(c for c in cells if "Kernel" in c and "(" in c)
+                    pre_order = "PipelinedKernel<1," in name or "PipelinedKernel<(bool)1," in name
+                    key = "edge_derivatives" if "EdgeDerivatives" in name else (
+                        "update_pre_partials" if pre_order else "update_partials")
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[cells[-2]]
+                    totals[key] = totals.get(key, 0.0) + float(cells[-1].replace(",", "")) * scale
+            if len(totals) == 3 and all(v > 0 for v in totals.values()):
+                return totals, ("ncu dram__bytes_read.sum + dram__bytes_write.sum of the three launches of one call "
+                                "sequence, measured in this run")
+        except (OSError, subprocess.SubprocessError, ValueError, KeyError, StopIteration):
+            pass
+    return None, None
+
+
+def _measure(n, P, C, repeats, order, probe=True):
     rng = np.random.default_rng(20261017)
     states = rng.integers(0, 4, size=(n, P)).astype(np.int32)
     states[rng.random(states.shape) < 0.01] = 4
@@ -64,6 +96,10 @@ def _measure(n, P, C, repeats, order):
 
     keep_a, post_ptr = beagle._i(post)
     keep_b, pre_ptr = beagle._i(pre)
+    if repeats < 0:  # (the probe process of measure_dram: one call sequence, three kernels)
+        beagle.log_likelihood_and_gradient(post, pre, lengths, q, rates, freqs, True, per_site=False)
+        beagle.close()
+        return None
     results = {"post_ms": [], "pre_ms": [], "derivatives_ms": [], "call_sequence_ms": []}
     for _ in range(repeats + 1):
         t0 = time.perf_counter()
@@ -94,21 +130,28 @@ def _measure(n, P, C, repeats, order):
     }
     # Two fractions per call.  `algorithmic_frac_of_peak`: SURVEY.md 8d's bytes (every partial through HBM)
     # over the time -- it exceeds 1 where the 126 MB L2 serves partials written a few ops earlier.
-    # `hbm_frac`: the DRAM bytes ncu measured for the same launch at this size (profiles/
-    # r02_beagle_shim_ncu_summary.json, committed with the kernels) over the time = real HBM utilisation.
+    # `hbm_frac`: the DRAM bytes of the same launch, measured by ncu IN THIS RUN on a probe process that makes
+    # one call sequence (else the committed capture profiles/r02_beagle_shim_ncu_summary.json, and
+    # `dram_source` says so), over the time = real HBM utilisation.
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm = json.load(open(peaks)).get("hbm_gbs") if os.path.exists(peaks) else None
-    summary_path = os.path.join(ROOT, "profiles", "r02_beagle_shim_ncu_summary.json")
-    measured = json.load(open(summary_path)).get("kernels_" + order, {}) if os.path.exists(summary_path) else {}
-    same_size = (n, P, C) == (100, 100000, 4)
+    dram, source = measure_dram(n, P, C, order) if probe else (None, None)
+    if dram is None:
+        summary_path = os.path.join(ROOT, "profiles", "r02_beagle_shim_ncu_summary.json")
+        committed = json.load(open(summary_path)).get("kernels_" + order, {}) if os.path.exists(summary_path) else {}
+        if (n, P, C) == (100, 100000, 4) and committed:
+            dram = {key: committed[key]["dram_bytes"] for key in committed}
+            source = "profiles/r02_beagle_shim_ncu_summary.json (committed ncu capture; not measured in this run)"
     if hbm:
         out["hbm_peak_GBps_measured"] = hbm
         for key in ("update_partials", "update_pre_partials", "edge_derivatives"):
             out[key]["algorithmic_frac_of_peak"] = out[key]["GBps"] / hbm
-            if same_size and key in measured:
-                out[key]["dram_GB_measured"] = measured[key]["dram_bytes"] / 1e9
-                out[key]["hbm_GBps"] = measured[key]["dram_bytes"] / out[key]["ms"] / 1e6
+            if dram and key in dram:
+                out[key]["dram_GB_measured"] = dram[key] / 1e9
+                out[key]["hbm_GBps"] = dram[key] / out[key]["ms"] / 1e6
                 out[key]["hbm_frac"] = out[key]["hbm_GBps"] / hbm
+        if dram:
+            out["dram_source"] = source
     beagle.close()
     return out
 
@@ -119,7 +162,11 @@ def main():
     parser.add_argument("--patterns", type=int, default=100000)
     parser.add_argument("--categories", type=int, default=4)
     parser.add_argument("--repeats", type=int, default=5)
+    parser.add_argument("--_probe", dest="probe", default=None, help=argparse.SUPPRESS)
     args = parser.parse_args()
+    if args.probe:  # the process measure_dram() profiles: one call sequence in the given op order
+        _measure(args.taxa, args.patterns, args.categories, -1, args.probe, probe=False)
+        return
     print(json.dumps(measure(args.taxa, args.patterns, args.categories, args.repeats)))
 
 
