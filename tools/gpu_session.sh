@@ -1,2 +1,4 @@
+# Development aid: the command list of one `gpurun -- 'bash tools/gpu_session.sh'` call (edited per session).
 mkdir -p gpurun_out
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --print-units base --kernel-name-base demangled -k "regex:UpdatePartialsPipelinedKernel|EdgeDerivativesKernel" -c 3 --csv --log-file gpurun_out/s66_probe.csv python tools/beagle_shim_bench.py --_probe libsbn --taxa 100 --patterns 100000 --categories 4 > gpurun_out/s66_probe.out 2>&1; tail -5 gpurun_out/s66_probe.out; cat gpurun_out/s66_probe.csv | cut -c1-400 | head -12
+(timeout 1500 python -m pytest tests -m gpu -x -q) > gpurun_out/s67_pytest.log 2>&1; tail -3 gpurun_out/s67_pytest.log
+(time python bench.py > gpurun_out/s67_bench.json) 2> gpurun_out/s67_bench.err; tail -4 gpurun_out/s67_bench.err; cut -c1-200 gpurun_out/s67_bench.json
