@@ -1,4 +1,3 @@
-# Development aid: the command list of one `gpurun -- 'bash tools/gpu_session.sh'` call (edited per session).
 mkdir -p gpurun_out
-(timeout 1500 python -m pytest tests -m gpu -x -q) > gpurun_out/s67_pytest.log 2>&1; tail -3 gpurun_out/s67_pytest.log
-(time python bench.py > gpurun_out/s67_bench.json) 2> gpurun_out/s67_bench.err; tail -4 gpurun_out/s67_bench.err; cut -c1-200 gpurun_out/s67_bench.json
+rm -f gpurun_out/ab.log
+TREES=592 ROUNDS=2 bash tools/ab.sh new logl4
