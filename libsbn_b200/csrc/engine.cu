@@ -1071,7 +1071,9 @@ std::unique_ptr<sbnb_engine> CreateEngine(const char* substitution, const char* 
   engine->range_end = pattern_count;
   engine->categories = engine->spec.category_count;
   engine->padded_categories = PadCategories(engine->categories);
-  Require(engine->padded_categories > 0, "At most 16 rate categories are supported.");
+  Require(engine->padded_categories > 0,
+          "At most 16 rate categories are supported by the fused tree walk (libhmsbeagle_b200.so, the "
+          "BEAGLE-compatible device library behind the unmodified FatBeagle, takes any number).");
   SBNB_CUDA(cudaStreamCreateWithFlags(&engine->stream, cudaStreamNonBlocking));
   SBNB_CUDA(cudaEventCreateWithFlags(&engine->staging_free, cudaEventDisableTiming));
   for (int i = 0; i < sbnb_engine::kWalkRing; i++) {
