@@ -51,7 +51,7 @@ def test_no_device_means_no_resource_not_a_cpu_fallback():
 @pytest.mark.gpu
 @pytest.mark.parametrize("order", ["libsbn", "node_id"])
 @pytest.mark.parametrize("categories,use_tip_states,rescaling", [(1, True, False), (4, True, True), (4, False, False),
-                                                                 (3, True, True), (4, True, False)])
+                                                                 (3, True, True), (4, True, False), (20, True, True)])
 def test_device_library_against_the_cpu_restatement(categories, use_tip_states, rescaling, order):
     rng = np.random.default_rng(categories * 10 + use_tip_states * 2 + rescaling)
     n, P = 13, 1003
