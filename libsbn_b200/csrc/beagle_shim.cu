@@ -149,7 +149,8 @@ __device__ __forceinline__ double OpTerm(const InstanceView& v, const DeviceOp& 
   return fmax(fmax(d[0], d[1]), fmax(d[2], d[3]));
 }
 
-// CT = 1, 2, 4, 8 or 16 rate categories: a thread owns K adjacent patterns of one category --
+// Up to 16 rate categories on CT = 1, 2, 4, 8 or 16 lanes per pattern (the next power of two;
+// spare lanes shadow category 0): a thread owns K adjacent patterns of one category --
 // category-major inside the warp, so the 32 / CT lanes of a category read consecutive patterns
 // (32 K bytes each: coalesced) -- for the whole op list of the call.  The walk is a chain of
 // dependent global-memory round trips per thread (ncu of the first version: 66 % of the
@@ -176,7 +177,7 @@ constexpr int kMatrixStride = 18;  // doubles between the category blocks of a s
 #endif
 __host__ __device__ constexpr int ChunkOps(int CT) { return CT <= 4 ? SBNB_SHIM_CHUNK : (CT == 8 ? SBNB_SHIM_CHUNK / 2 : SBNB_SHIM_CHUNK / 4); }
 
-template <bool PRE, int CT, int K>
+template <bool PRE, int CT, int K, bool PADDED>
 __global__ void __launch_bounds__(kPipeBlock, K == 1 ? kPipeMinBlocks : (kPipeMinBlocks + 1) / 2) UpdatePartialsPipelinedKernel(const InstanceView v,
                                                                        const DeviceOp* __restrict__ ops, int op_count,
                                                                        int cumulative, int cumulative_in_register) {
@@ -189,7 +190,14 @@ __global__ void __launch_bounds__(kPipeBlock, K == 1 ? kPipeMinBlocks : (kPipeMi
   __shared__ __align__(16) DeviceOp s_ops[kChunk];
   __shared__ __align__(16) double s_matrix[kChunk * kOpMatrixDoubles];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = lane / kPerWarp;
+  // v.C <= CT categories on CT lanes per pattern: the lanes past the last category shadow
+  // category 0 (same values: the maximum over the lanes does not change) and store nothing.
+  // (PADDED = false: v.C == CT, and none of this costs anything -- with the run-time form the
+  //  pre-order update of 4 categories measured 13 % slower)
+  const int category_lane = lane / kPerWarp;
+  const bool padding_lane = PADDED && category_lane >= v.C;
+  const int c = padding_lane ? 0 : category_lane;
+  const int categories = PADDED ? v.C : CT;
   // (the trip count is the same for every thread of a block: the chunk loop has barriers)
   for (int64_t base = static_cast<int64_t>(blockIdx.x) * kPipeBlockPatterns; base < v.P;
        base += static_cast<int64_t>(gridDim.x) * kPipeBlockPatterns) {
@@ -201,8 +209,8 @@ __global__ void __launch_bounds__(kPipeBlock, K == 1 ? kPipeMinBlocks : (kPipeMi
     int pattern[K], live[K];
 #pragma unroll
     for (int j = 0; j < K; j++) {
-      live[j] = first + j < v.P;
-      pattern[j] = static_cast<int>(live[j] ? first + j : v.P - 1);  // (idle slots shadow the last pattern)
+      pattern[j] = static_cast<int>(first + j < v.P ? first + j : v.P - 1);  // (idle slots shadow the last pattern)
+      live[j] = first + j < v.P && !padding_lane;
       elem[j] = (static_cast<int64_t>(c) * v.P + pattern[j]) * kStates;
       asm volatile("" : "+l"(elem[j]), "+r"(pattern[j]), "+r"(live[j]));
     }
@@ -294,8 +302,9 @@ __global__ void __launch_bounds__(kPipeBlock, K == 1 ? kPipeMinBlocks : (kPipeMi
           const DeviceOp& op = ops[chunk_begin + o];
           const int flags = op.flags;
           const int matrix = which ? op.matrix2 : op.matrix1;
-          s_matrix[o * kOpMatrixDoubles + ((flags & (which ? kChild2Compact : kChild1Compact)) ? transposed : plain)] =
-              v.matrix[(static_cast<size_t>(matrix) * CT + cc) * 16 + entry];
+          if (cc < categories)
+            s_matrix[o * kOpMatrixDoubles + ((flags & (which ? kChild2Compact : kChild1Compact)) ? transposed : plain)] =
+                v.matrix[(static_cast<size_t>(matrix) * categories + cc) * 16 + entry];
         }
       } else {
         for (int e = threadIdx.x; e < chunk_ops * kOpEntries; e += kPipeBlock) {
@@ -303,9 +312,10 @@ __global__ void __launch_bounds__(kPipeBlock, K == 1 ? kPipeMinBlocks : (kPipeMi
           const DeviceOp& op = ops[chunk_begin + o];
           const bool transposed = op.flags & (which ? kChild2Compact : kChild1Compact);
           const int matrix = which ? op.matrix2 : op.matrix1;
-          s_matrix[o * kOpMatrixDoubles + (which * CT + cc) * kMatrixStride +
-                   (transposed ? (entry & 3) * 4 + (entry >> 2) : entry)] =
-              v.matrix[(static_cast<size_t>(matrix) * CT + cc) * 16 + entry];
+          if (cc < categories)
+            s_matrix[o * kOpMatrixDoubles + (which * CT + cc) * kMatrixStride +
+                     (transposed ? (entry & 3) * 4 + (entry >> 2) : entry)] =
+                v.matrix[(static_cast<size_t>(matrix) * categories + cc) * 16 + entry];
         }
       }
       __syncthreads();
@@ -380,7 +390,7 @@ __global__ void __launch_bounds__(kPipeBlock, K == 1 ? kPipeMinBlocks : (kPipeMi
 #pragma unroll
             for (int i = 0; i < 4; i++) d[j][i] *= inverse;
           }
-          if (c == 0) {
+          if (category_lane == 0) {
 #pragma unroll
             for (int j = 0; j < K; j++)
               if (live[j]) v.scale[op.scale_at + pattern[j]] = largest[j];
@@ -389,9 +399,9 @@ __global__ void __launch_bounds__(kPipeBlock, K == 1 ? kPipeMinBlocks : (kPipeMi
             if (cumulative_in_register) {
 #pragma unroll
               for (int j = 0; j < K; j++)
-                if (c == pending) held[j] = largest[j];
+                if (category_lane == pending) held[j] = largest[j];
               if (++pending == CT) flush_logarithms();
-            } else if (c == 0) {
+            } else if (category_lane == 0) {
 #pragma unroll
               for (int j = 0; j < K; j++)
                 if (live[j]) v.scale[static_cast<int64_t>(cumulative) * v.P + pattern[j]] += log(largest[j]);
@@ -405,7 +415,7 @@ __global__ void __launch_bounds__(kPipeBlock, K == 1 ? kPipeMinBlocks : (kPipeMi
     }
     if (cumulative >= 0 && cumulative_in_register) {
       if (pending > 0) flush_logarithms();
-      if (c == 0) {
+      if (category_lane == 0) {
 #pragma unroll
         for (int j = 0; j < K; j++)
           if (live[j]) v.scale[static_cast<int64_t>(cumulative) * v.P + pattern[j]] = cum[j];
@@ -755,22 +765,28 @@ int UpdatePartials(int instance, const BeagleOperation* operations, int count, i
   SHIM_CUDA(cudaEventRecord(inst->begin, inst->stream));
   // K adjacent patterns per thread (SBNB_BEAGLE_PATTERNS_PER_THREAD = 2: twice the loads in flight
   // per thread, half the matrix reads, half the threads).
-  const int64_t lane_threads = static_cast<int64_t>(inst->P) * inst->C;
+  int lanes = 1;  // lanes per pattern: the category count rounded up to a power of two (more than 16: the generic kernel)
+  while (lanes < inst->C) lanes <<= 1;
+  const int64_t lane_threads = static_cast<int64_t>(inst->P) * lanes;
   int K = 1;  // (two measured slower on the pre-order list and the same on the post-order one at 100k x 4)
   if (const char* forced = std::getenv("SBNB_BEAGLE_PATTERNS_PER_THREAD")) K = std::atoi(forced) >= 2 ? 2 : 1;
+  if (lanes != inst->C) K = 1;  // (the padded form exists with one pattern per thread)
   const int lane_blocks =
       static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((lane_threads + kPipeBlock * K - 1) / (kPipeBlock * K), 1 << 30)));
 #define SHIM_LANES(CT)                                                                                        \
   case CT:                                                                                                    \
-    if (K == 2) {                                                                                             \
-      UpdatePartialsPipelinedKernel<PRE, CT, 2><<<lane_blocks, kPipeBlock, 0, inst->stream>>>(                    \
+    if (inst->C != CT) {                                                                                      \
+      UpdatePartialsPipelinedKernel<PRE, CT, 1, true><<<lane_blocks, kPipeBlock, 0, inst->stream>>>(          \
+          view, inst->ops.ptr, count, cumulative_index, cumulative_in_register);                              \
+    } else if (K == 2) {                                                                                      \
+      UpdatePartialsPipelinedKernel<PRE, CT, 2, false><<<lane_blocks, kPipeBlock, 0, inst->stream>>>(         \
           view, inst->ops.ptr, count, cumulative_index, cumulative_in_register);                              \
     } else {                                                                                                  \
-      UpdatePartialsPipelinedKernel<PRE, CT, 1><<<lane_blocks, kPipeBlock, 0, inst->stream>>>(                    \
+      UpdatePartialsPipelinedKernel<PRE, CT, 1, false><<<lane_blocks, kPipeBlock, 0, inst->stream>>>(         \
           view, inst->ops.ptr, count, cumulative_index, cumulative_in_register);                              \
     }                                                                                                         \
     break;
-  switch (inst->C) {
+  switch (lanes) {
     SHIM_LANES(1)
     SHIM_LANES(2)
     SHIM_LANES(4)
